@@ -1,0 +1,134 @@
+"""ctypes binding of libadsb200.so -- the C ABI declared in include/adsb200.h.
+
+Nothing here computes: every function forwards to the shared library, and the library has no CPU
+fallback for the device entry points.  Importing this module never touches /root/reference or
+oracle/.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libadsb200.so")
+
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_ll = ctypes.c_longlong
+dp = ctypes.POINTER(c_dbl)
+ip = ctypes.POINTER(c_int)
+llp = ctypes.POINTER(c_ll)
+vp = ctypes.c_void_p
+
+MAX_SLOTS = 4
+MAX_BUFFERS = 8
+RHS_COLLAPSED = 0
+RHS_QUADRATURE = 1
+
+
+class AdsbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"adsb error {code}: {message}")
+        self.code = code
+
+
+class Form(ctypes.Structure):
+    """adsb_form: rhs = alpha*(u,v) - sum_k beta[k]*(d_k u, d_k v) + gamma*F."""
+    _fields_ = [("alpha", c_dbl), ("beta", c_dbl * 3), ("gamma", c_dbl), ("forcing_buf", c_int),
+                ("method", c_int)]
+
+    @classmethod
+    def make(cls, alpha=1.0, beta=(0.0, 0.0, 0.0), gamma=0.0, forcing_buf=-1, method=RHS_COLLAPSED):
+        b = list(beta) + [0.0] * (3 - len(beta))
+        return cls(alpha, (c_dbl * 3)(*b), gamma, forcing_buf, method)
+
+
+class Substep(ctypes.Structure):
+    _fields_ = [("form", Form), ("slots", c_int * 3), ("fix_axis", c_int), ("fix_buf", c_int)]
+
+    @classmethod
+    def make(cls, form, slots=(0, 0, 0), fix_axis=-1, fix_buf=-1):
+        s = list(slots) + [0] * (3 - len(slots))
+        return cls(form, (c_int * 3)(*s), fix_axis, fix_buf)
+
+
+class View(ctypes.Structure):
+    _fields_ = [("n", c_int * 3), ("s", c_ll * 3)]
+
+    @classmethod
+    def make(cls, n, s):
+        n = list(n) + [1] * (3 - len(n))
+        s = list(s) + [int(np.prod(n))] * (3 - len(s))
+        return cls((c_int * 3)(*n), (c_ll * 3)(*s))
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "adsb_abi_version": (c_int, []),
+    "adsb_last_error": (ctypes.c_char_p, []),
+    "adsb_gauss": (c_int, [c_int, dp, dp]),
+    "adsb_knots": (c_int, [c_int, c_int, c_dbl, c_dbl, dp]),
+    "adsb_find_span": (c_int, [c_dbl, dp, c_int, c_int]),
+    "adsb_basis_ders": (c_int, [c_int, c_dbl, dp, c_int, c_int, dp]),
+    "adsb_basis_tables": (c_int, [c_int, c_int, c_dbl, c_dbl, c_int, c_int, dp, dp, dp, dp, ip]),
+    "adsb_matrix_1d": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int, dp]),
+    "adsb_band_factorize": (c_int, [c_int, c_int, c_int, dp, c_int, ip]),
+    "adsb_create": (c_int, [c_int, ip, ip, ip, c_int, ctypes.POINTER(vp)]),
+    "adsb_destroy": (c_int, [vp]),
+    "adsb_set_stream": (c_int, [vp, vp]),
+    "adsb_synchronize": (c_int, [vp]),
+    "adsb_set_axis_tables": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, dp, dp, dp, dp, ip]),
+    "adsb_set_axis_factor": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_int, dp, ip]),
+    "adsb_upload": (c_int, [vp, c_int, dp]),
+    "adsb_download": (c_int, [vp, c_int, dp]),
+    "adsb_swap": (c_int, [vp, c_int, c_int]),
+    "adsb_zero": (c_int, [vp, c_int]),
+    "adsb_bind": (c_int, [vp, c_int, vp]),
+    "adsb_device_ptr": (vp, [vp, c_int]),
+    "adsb_set_plane": (c_int, [vp, c_int, c_int, c_int, dp]),
+    "adsb_compute_rhs": (c_int, [vp, ctypes.POINTER(Form), c_int, c_int]),
+    "adsb_load_tensor": (c_int, [vp, c_int, c_int, c_int]),
+    "adsb_project_init": (c_int, [vp, c_int, c_int]),
+    "adsb_solve": (c_int, [vp, c_int, ip]),
+    "adsb_sweep": (c_int, [vp, c_int, c_int, c_int]),
+    "adsb_step": (c_int, [vp, c_int, c_int, ctypes.POINTER(Substep), c_int, c_int]),
+    "adsb_enable_timing": (c_int, [vp, c_int]),
+    "adsb_stage_times": (c_int, [vp, dp]),
+    "adsb_launch_count": (c_ll, [vp]),
+    "adsb_sweep_view": (c_int, [vp, c_int, c_int, vp, ctypes.POINTER(View), llp, vp, ctypes.POINTER(View), llp]),
+    "adsb_sweep_plan": (c_int, [c_int, c_int, c_int, c_int, dp, ip, ip, dp, ip, dp, dp, dp, dp, dp]),
+    "adsb_rhs_view": (c_int, [vp, ctypes.POINTER(Form), vp, ctypes.POINTER(View), ip, vp, vp,
+                              ctypes.POINTER(View), ip]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+_lib = None
+
+
+def load():
+    """Load libadsb200.so (built by __graft_entry__.build() / make -C iga_ads_b200/csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise AdsbError(rc, load().adsb_last_error().decode())
+    return rc
+
+
+def d_(a):
+    return a.ctypes.data_as(dp)
+
+
+def i_(a):
+    return a.ctypes.data_as(ip)

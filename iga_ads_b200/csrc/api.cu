@@ -1,0 +1,668 @@
+// api.cu -- device context and the C ABI of libadsb200.so (see include/adsb200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "adsb200.h"
+#include "internal.hpp"
+#include "kernels.cuh"
+
+using namespace adsb;
+
+namespace {
+
+struct DevFactor {
+    bool set = false;
+    SweepFactor f{};
+    std::vector<void*> allocs;
+};
+
+struct AxisData {
+    bool tables = false;
+    int p = 0, elements = 0, q = 0, ders = 0, n = 0;
+    std::vector<double> bt, xq, w, J;  // host copies (layout of adsb_basis_tables)
+    double* d_M = nullptr;             // [n][2p+1] Gram rows
+    double* d_S = nullptr;             // [n][2p+1] stiffness rows
+    double* d_bt = nullptr;            // device copy of bt
+    double* d_xq = nullptr;
+    double* d_wJ = nullptr;            // [elements][q] w[k]*J[e]
+    double* d_w = nullptr;
+    double* d_J = nullptr;
+    DevFactor fac[ADSB_MAX_SLOTS];
+};
+
+struct TimedSpan {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct adsb_ctx {
+    int ndim = 0;
+    int ng[3] = {1, 1, 1}, lo[3] = {0, 0, 0}, cnt[3] = {1, 1, 1};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    AxisData ax[3];
+    double* buf[ADSB_MAX_BUFFERS] = {};
+    bool owned[ADSB_MAX_BUFFERS] = {};
+    std::map<std::vector<long long>, long long*> off_cache;
+    bool timing = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> free_events;
+    double acc_ms[5] = {};
+    long long launches = 0;
+    size_t local_size() const { return (size_t) cnt[0] * cnt[1] * cnt[2]; }
+};
+
+namespace {
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(ADSB_ENODEVICE, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+int select_device(adsb_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return ADSB_OK;
+}
+
+template <typename T>
+int upload_vec(const std::vector<T>& h, size_t padded, T** d, std::vector<void*>* track) {
+    std::vector<T> tmp(h);
+    tmp.resize(std::max(padded, h.size()), T{});
+    CU(cudaMalloc((void**) d, tmp.size() * sizeof(T)));
+    if (track) track->push_back(*d);
+    CU(cudaMemcpy(*d, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ADSB_OK;
+}
+
+void free_factor(DevFactor& f) {
+    for (void* p : f.allocs) cudaFree(p);
+    f.allocs.clear();
+    f.set = false;
+}
+
+int ensure_buf(adsb_ctx* c, int b) {
+    if (b < 0 || b >= ADSB_MAX_BUFFERS) return fail(ADSB_EINVAL, "buffer id out of range");
+    if (!c->buf[b]) {
+        CU(cudaMalloc((void**) &c->buf[b], c->local_size() * sizeof(double)));
+        c->owned[b] = true;
+    }
+    return ADSB_OK;
+}
+
+cudaEvent_t get_event(adsb_ctx* c) {
+    if (!c->free_events.empty()) {
+        cudaEvent_t e = c->free_events.back();
+        c->free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    adsb_ctx* c;
+    TimedSpan s{};
+    bool on;
+    StageTimer(adsb_ctx* ctx, int stage) : c(ctx), on(ctx->timing) {
+        if (on) {
+            s.stage = stage;
+            s.a = get_event(c);
+            s.b = get_event(c);
+            cudaEventRecord(s.a, c->stream);
+        }
+    }
+    ~StageTimer() {
+        if (on) {
+            cudaEventRecord(s.b, c->stream);
+            c->spans.push_back(s);
+        }
+    }
+};
+
+int pick_nl(int S) {
+    int nl = 64;
+    while (nl > 4 && nl * S > 384) nl >>= 1;
+    return nl;
+}
+
+int get_offsets(adsb_ctx* c, const long long* host, int n, const long long** dev) {
+    *dev = nullptr;
+    if (!host) return ADSB_OK;
+    std::vector<long long> key(host, host + n);
+    auto it = c->off_cache.find(key);
+    if (it == c->off_cache.end()) {
+        long long* d = nullptr;
+        CU(cudaMalloc((void**) &d, n * sizeof(long long)));
+        CU(cudaMemcpy(d, host, n * sizeof(long long), cudaMemcpyHostToDevice));
+        it = c->off_cache.emplace(std::move(key), d).first;
+    }
+    *dev = it->second;
+    return ADSB_OK;
+}
+
+// sweep along `axis` of a view; see adsb_sweep_view
+int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view& vi,
+               const long long* off_in_h, double* out, const adsb_view& vo, const long long* off_out_h) {
+    if (axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "sweep: bad axis");
+    if (slot < 0 || slot >= ADSB_MAX_SLOTS || !c->ax[axis].fac[slot].set)
+        return fail(ADSB_ESTATE, "sweep: no factor uploaded for this axis/slot");
+    const SweepFactor& F = c->ax[axis].fac[slot].f;
+    for (int d = 0; d < 3; ++d)
+        if (vi.n[d] != vo.n[d]) return fail(ADSB_EINVAL, "sweep: in/out extents differ");
+    if (vi.n[axis] != F.n) return fail(ADSB_EINVAL, "sweep: the view does not span the whole axis");
+    const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+    const long long* off_in = nullptr;
+    const long long* off_out = nullptr;
+    if (int rc = get_offsets(c, off_in_h, F.n, &off_in)) return rc;
+    if (int rc = get_offsets(c, off_out_h, F.n, &off_out)) return rc;
+    SweepGeom G{};
+    G.in = in;
+    G.out = out;
+    G.off_in = off_in;
+    G.off_out = off_out;
+    G.sj_in = vi.s[axis];
+    G.sj_out = vo.s[axis];
+    const bool contig = !off_in && !off_out && vi.s[axis] == 1 && vo.s[axis] == 1 && F.n > 1;
+    int l0, l1;
+    if (contig) {
+        // lines enumerated along the perpendicular axis with the smaller stride first
+        l0 = (vi.s[a] <= vi.s[b]) ? a : b;
+    } else {
+        // lanes along the perpendicular axis with unit stride (or the smaller one)
+        l0 = (vi.s[a] <= vi.s[b]) ? a : b;
+        if (vi.n[l0] == 1) l0 = (l0 == a) ? b : a;
+    }
+    l1 = (l0 == a) ? b : a;
+    G.L0 = vi.n[l0];
+    G.L1 = vi.n[l1];
+    G.s0_in = vi.s[l0];
+    G.s0_out = vo.s[l0];
+    G.s1_in = vi.s[l1];
+    G.s1_out = vo.s[l1];
+    G.pitch = F.n | 1;
+    int NL = pick_nl(F.S);
+    if (contig) {
+        while (NL > 1 && sweep_smem_bytes(F, true, NL, G.pitch) > 100 * 1024) NL >>= 1;
+        if (sweep_smem_bytes(F, true, NL, G.pitch) > 220 * 1024)
+            return fail(ADSB_EINVAL, "sweep: line too long for the shared-memory staged x sweep");
+    }
+    if (NL * F.S > 512) return fail(ADSB_EINVAL, "sweep: axis too long for the compiled chunking (n <= 4224)");
+    if (G.L1 > 65535) return fail(ADSB_EINVAL, "sweep: outer extent beyond grid limits");
+    StageTimer t(c, 1 + axis);
+    cudaError_t e = (cudaError_t) launch_sweep(F, G, contig, NL, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sweep kernel launch");
+    c->launches++;
+    return ADSB_OK;
+}
+
+adsb_view local_view(const adsb_ctx* c) {
+    adsb_view v{};
+    for (int d = 0; d < 3; ++d) v.n[d] = c->cnt[d];
+    v.s[0] = 1;
+    v.s[1] = c->cnt[0];
+    v.s[2] = (long long) c->cnt[0] * c->cnt[1];
+    return v;
+}
+
+int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view& vi, const int* in_lo,
+             const double* forcing, double* out, const adsb_view& vo, const int* out_lo) {
+    if (f.method != ADSB_RHS_COLLAPSED)
+        return fail(ADSB_EINVAL, "compute_rhs: only ADSB_RHS_COLLAPSED is built in this version");
+    for (int d = 0; d < c->ndim; ++d)
+        if (!c->ax[d].tables) return fail(ADSB_ESTATE, "compute_rhs: axis tables not uploaded");
+    RhsOps ops{};
+    ops.Mx = c->ax[0].d_M;
+    ops.Sx = c->ax[0].d_S;
+    ops.My = c->ax[1].d_M;
+    ops.Sy = c->ax[1].d_S;
+    ops.Mz = c->ndim == 3 ? c->ax[2].d_M : nullptr;
+    ops.Sz = c->ndim == 3 ? c->ax[2].d_S : nullptr;
+    RhsGeom g{};
+    g.in = in;
+    g.out = out;
+    g.forcing = (f.gamma != 0.0) ? forcing : nullptr;
+    for (int d = 0; d < 3; ++d) {
+        ops.p[d] = d < c->ndim ? c->ax[d].p : 0;
+        ops.n[d] = c->ng[d];
+        g.si[d] = vi.s[d];
+        g.so[d] = vo.s[d];
+        g.in_lo[d] = in_lo[d];
+        g.in_n[d] = vi.n[d];
+        g.out_lo[d] = out_lo[d];
+        g.out_n[d] = vo.n[d];
+        g.beta[d] = d < c->ndim ? f.beta[d] : 0.0;
+        if (d < c->ndim) {
+            // the input box must cover the output box widened by p, clipped to the domain
+            const int need_lo = std::max(0, out_lo[d] - c->ax[d].p);
+            const int need_hi = std::min(c->ng[d], out_lo[d] + vo.n[d] + c->ax[d].p);
+            if (in_lo[d] > need_lo || in_lo[d] + vi.n[d] < need_hi)
+                return fail(ADSB_EINVAL, "compute_rhs: input box lacks the p-wide halo of the output box");
+        }
+    }
+    g.alpha = f.alpha;
+    g.gamma = f.gamma;
+    StageTimer t(c, 0);
+    cudaError_t e = (cudaError_t) launch_rhs_collapsed(c->ndim, ops, g, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "rhs kernel launch");
+    c->launches++;
+    return ADSB_OK;
+}
+
+int rows_from_band(int n, int p, const std::vector<double>& ab, std::vector<double>& rows) {
+    const int W = 2 * p + 1, ldab = 3 * p + 1;
+    rows.assign((size_t) n * W, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int m = 0; m < W; ++m) {
+            const int j = i - p + m;
+            if (j >= 0 && j < n) rows[(size_t) i * W + m] = ab[(size_t) j * ldab + 2 * p + i - j];
+        }
+    return ADSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int adsb_create(int ndim, const int* n_global, const int* lo, const int* cnt, int device, adsb_ctx** out) {
+    if (!out || !n_global || (ndim != 2 && ndim != 3)) return fail(ADSB_EINVAL, "create: ndim must be 2 or 3");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ADSB_ENODEVICE, "create: no CUDA device (libadsb200 has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(ADSB_EINVAL, "create: bad device ordinal");
+    auto* c = new adsb_ctx;
+    c->ndim = ndim;
+    c->device = device;
+    for (int d = 0; d < ndim; ++d) {
+        c->ng[d] = n_global[d];
+        c->lo[d] = lo ? lo[d] : 0;
+        c->cnt[d] = cnt ? cnt[d] : n_global[d];
+        if (c->ng[d] < 1 || c->lo[d] < 0 || c->cnt[d] < 1 || c->lo[d] + c->cnt[d] > c->ng[d]) {
+            delete c;
+            return fail(ADSB_EINVAL, "create: bad extents");
+        }
+    }
+    if (int rc = select_device(c)) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return ADSB_OK;
+}
+
+int adsb_destroy(adsb_ctx* c) {
+    if (!c) return ADSB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& a : c->ax) {
+        cudaFree(a.d_M);
+        cudaFree(a.d_S);
+        cudaFree(a.d_bt);
+        cudaFree(a.d_xq);
+        cudaFree(a.d_wJ);
+        cudaFree(a.d_w);
+        cudaFree(a.d_J);
+        for (auto& f : a.fac) free_factor(f);
+    }
+    for (int b = 0; b < ADSB_MAX_BUFFERS; ++b)
+        if (c->owned[b]) cudaFree(c->buf[b]);
+    for (auto& kv : c->off_cache) cudaFree(kv.second);
+    for (auto& s : c->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    for (auto e : c->free_events) cudaEventDestroy(e);
+    delete c;
+    return ADSB_OK;
+}
+
+int adsb_set_stream(adsb_ctx* c, void* s) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    c->stream = (cudaStream_t) s;
+    return ADSB_OK;
+}
+
+int adsb_synchronize(adsb_ctx* c) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    CU(cudaStreamSynchronize(c->stream));
+    return ADSB_OK;
+}
+
+int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int ders, const double* b_flat,
+                         const double* xq, const double* w, const double* J, const int* first_dof) {
+    if (!c || axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "set_axis_tables: bad axis");
+    if (p < 1 || p > 5) return fail(ADSB_EINVAL, "set_axis_tables: device kernels are built for 1 <= p <= 5");
+    if (elements + p != c->ng[axis]) return fail(ADSB_EINVAL, "set_axis_tables: elements + p != n_global[axis]");
+    if (ders < 1) return fail(ADSB_EINVAL, "set_axis_tables: first derivatives are required");
+    for (int e = 0; e < elements; ++e)
+        if (first_dof[e] != e) return fail(ADSB_EINVAL, "set_axis_tables: repeated knots are not supported");
+    if (int rc = select_device(c)) return rc;
+    AxisData& a = c->ax[axis];
+    a.p = p;
+    a.elements = elements;
+    a.q = q;
+    a.ders = ders;
+    a.n = elements + p;
+    const size_t nb = (size_t) elements * q * (ders + 1) * (p + 1);
+    a.bt.assign(b_flat, b_flat + nb);
+    a.xq.assign(xq, xq + (size_t) elements * q);
+    a.w.assign(w, w + q);
+    a.J.assign(J, J + elements);
+    std::vector<double> ab((size_t) (3 * p + 1) * a.n), rows;
+    cudaFree(a.d_M);
+    cudaFree(a.d_S);
+    cudaFree(a.d_bt);
+    cudaFree(a.d_xq);
+    cudaFree(a.d_wJ);
+    cudaFree(a.d_w);
+    cudaFree(a.d_J);
+    a.d_M = a.d_S = a.d_bt = a.d_xq = a.d_wJ = a.d_w = a.d_J = nullptr;
+    if (int rc = matrix_from_tables(0, 0.0, p, elements, q, ders, b_flat, w, J, ab.data())) return rc;
+    rows_from_band(a.n, p, ab, rows);
+    if (int rc = upload_vec(rows, 0, &a.d_M, nullptr)) return rc;
+    if (int rc = matrix_from_tables(1, 0.0, p, elements, q, ders, b_flat, w, J, ab.data())) return rc;
+    rows_from_band(a.n, p, ab, rows);
+    if (int rc = upload_vec(rows, 0, &a.d_S, nullptr)) return rc;
+    if (int rc = upload_vec(a.bt, 0, &a.d_bt, nullptr)) return rc;
+    if (int rc = upload_vec(a.xq, 0, &a.d_xq, nullptr)) return rc;
+    std::vector<double> wJ((size_t) elements * q);
+    for (int e = 0; e < elements; ++e)
+        for (int k = 0; k < q; ++k) wJ[(size_t) e * q + k] = w[k] * J[e];
+    if (int rc = upload_vec(wJ, 0, &a.d_wJ, nullptr)) return rc;
+    if (int rc = upload_vec(a.w, 0, &a.d_w, nullptr)) return rc;
+    if (int rc = upload_vec(a.J, 0, &a.d_J, nullptr)) return rc;
+    a.tables = true;
+    return ADSB_OK;
+}
+
+int adsb_set_axis_factor(adsb_ctx* c, int axis, int slot, int n, int kl, int ku, int ldab, const double* ab,
+                         const int* ipiv) {
+    if (!c || axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "set_axis_factor: bad axis");
+    if (slot < 0 || slot >= ADSB_MAX_SLOTS) return fail(ADSB_EINVAL, "set_axis_factor: bad slot");
+    if (n != c->ng[axis]) return fail(ADSB_EINVAL, "set_axis_factor: n != n_global[axis]");
+    if (kl < 0 || ku < 0 || ldab < 2 * kl + ku + 1) return fail(ADSB_EINVAL, "set_axis_factor: bad band shape");
+    if (int rc = select_device(c)) return rc;
+    SweepPlan P;
+    if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, P)) return rc;
+    DevFactor& D = c->ax[axis].fac[slot];
+    CU(cudaStreamSynchronize(c->stream));
+    free_factor(D);
+    const size_t rows = (size_t) P.S * P.CH;
+    double *Lm, *Ut, *rinv, *Phi, *Psi, *T;
+    int* pv;
+    if (int rc = upload_vec(P.Lm, rows * P.KL, &Lm, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.pv, rows, &pv, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.Ut, rows * P.KD, &Ut, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.rinv, rows, &rinv, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.Phi, rows * P.KL, &Phi, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.Psi, rows * P.KD, &Psi, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.T, 0, &T, &D.allocs)) return rc;
+    D.f = SweepFactor{Lm, pv, Ut, rinv, Phi, Psi, T, P.n, P.S, P.KL, P.KD, P.piv};
+    D.set = true;
+    return ADSB_OK;
+}
+
+int adsb_upload(adsb_ctx* c, int b, const double* host) {
+    if (!c || !host) return fail(ADSB_EINVAL, "upload: null argument");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, b)) return rc;
+    CU(cudaMemcpyAsync(c->buf[b], host, c->local_size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ADSB_OK;
+}
+
+int adsb_download(adsb_ctx* c, int b, double* host) {
+    if (!c || !host) return fail(ADSB_EINVAL, "download: null argument");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "download: buffer not allocated");
+    if (int rc = select_device(c)) return rc;
+    CU(cudaMemcpyAsync(host, c->buf[b], c->local_size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ADSB_OK;
+}
+
+int adsb_swap(adsb_ctx* c, int a, int b) {
+    if (!c || a < 0 || b < 0 || a >= ADSB_MAX_BUFFERS || b >= ADSB_MAX_BUFFERS)
+        return fail(ADSB_EINVAL, "swap: bad buffer id");
+    std::swap(c->buf[a], c->buf[b]);
+    std::swap(c->owned[a], c->owned[b]);
+    return ADSB_OK;
+}
+
+int adsb_zero(adsb_ctx* c, int b) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, b)) return rc;
+    CU(cudaMemsetAsync(c->buf[b], 0, c->local_size() * sizeof(double), c->stream));
+    return ADSB_OK;
+}
+
+int adsb_bind(adsb_ctx* c, int b, double* p) {
+    if (!c || b < 0 || b >= ADSB_MAX_BUFFERS) return fail(ADSB_EINVAL, "bind: bad buffer id");
+    if (c->owned[b]) cudaFree(c->buf[b]);
+    c->buf[b] = p;
+    c->owned[b] = false;
+    return ADSB_OK;
+}
+
+double* adsb_device_ptr(adsb_ctx* c, int b) {
+    if (!c || b < 0 || b >= ADSB_MAX_BUFFERS) return nullptr;
+    if (select_device(c) || ensure_buf(c, b)) return nullptr;
+    return c->buf[b];
+}
+
+int adsb_set_plane(adsb_ctx* c, int b, int axis, int idx, const double* values) {
+    if (!c || axis < 0 || axis >= c->ndim || idx < 0 || idx >= c->cnt[axis])
+        return fail(ADSB_EINVAL, "set_plane: bad axis/index");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "set_plane: buffer not allocated");
+    if (int rc = select_device(c)) return rc;
+    adsb_view v = local_view(c);
+    size_t count = c->local_size() / c->cnt[axis];
+    double* d = nullptr;
+    CU(cudaMalloc((void**) &d, count * sizeof(double)));
+    CU(cudaMemcpyAsync(d, values, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    cudaError_t e = (cudaError_t) launch_set_plane(c->buf[b], v.s, v.n, axis, idx, d, c->stream);
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "set_plane kernel");
+    return ADSB_OK;
+}
+
+int adsb_compute_rhs(adsb_ctx* c, const adsb_form* f, int src, int dst) {
+    if (!c || !f) return fail(ADSB_EINVAL, "compute_rhs: null argument");
+    if (src == dst) return fail(ADSB_EINVAL, "compute_rhs: src and dst must differ");
+    if (src < 0 || src >= ADSB_MAX_BUFFERS || !c->buf[src]) return fail(ADSB_ESTATE, "compute_rhs: src not allocated");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, dst)) return rc;
+    const double* forcing = nullptr;
+    if (f->gamma != 0.0) {
+        if (f->forcing_buf < 0 || f->forcing_buf >= ADSB_MAX_BUFFERS || !c->buf[f->forcing_buf])
+            return fail(ADSB_ESTATE, "compute_rhs: forcing buffer not allocated");
+        forcing = c->buf[f->forcing_buf];
+    }
+    adsb_view v = local_view(c);
+    return rhs_impl(c, *f, c->buf[src], v, c->lo, forcing, c->buf[dst], v, c->lo);
+}
+
+int adsb_rhs_view(adsb_ctx* c, const adsb_form* f, const double* in, const adsb_view* vin, const int* in_lo,
+                  const double* forcing, double* out, const adsb_view* vout, const int* out_lo) {
+    if (!c || !f || !in || !out || !vin || !vout || !in_lo || !out_lo)
+        return fail(ADSB_EINVAL, "rhs_view: null argument");
+    if (int rc = select_device(c)) return rc;
+    return rhs_impl(c, *f, in, *vin, in_lo, forcing, out, *vout, out_lo);
+}
+
+int adsb_sweep_view(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view* vin,
+                    const long long* row_off_in, double* out, const adsb_view* vout, const long long* row_off_out) {
+    if (!c || !in || !out || !vin || !vout) return fail(ADSB_EINVAL, "sweep_view: null argument");
+    if (int rc = select_device(c)) return rc;
+    return sweep_impl(c, axis, slot, in, *vin, row_off_in, out, *vout, row_off_out);
+}
+
+int adsb_sweep(adsb_ctx* c, int b, int axis, int slot) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "sweep: buffer not allocated");
+    if (axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "sweep: bad axis");
+    if (c->cnt[axis] != c->ng[axis]) return fail(ADSB_ESTATE, "sweep: this context does not own whole lines of the axis");
+    if (int rc = select_device(c)) return rc;
+    adsb_view v = local_view(c);
+    return sweep_impl(c, axis, slot, c->buf[b], v, nullptr, c->buf[b], v, nullptr);
+}
+
+int adsb_solve(adsb_ctx* c, int b, const int* slots) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    for (int d = 0; d < c->ndim; ++d)
+        if (int rc = adsb_sweep(c, b, d, slots ? slots[d] : 0)) return rc;
+    return ADSB_OK;
+}
+
+int adsb_step(adsb_ctx* c, int u, int up, const adsb_substep* sub, int nsub, int nsteps) {
+    if (!c || !sub || nsub < 1 || nsteps < 0) return fail(ADSB_EINVAL, "step: bad arguments");
+    for (int it = 0; it < nsteps; ++it) {
+        for (int s = 0; s < nsub; ++s) {
+            if (int rc = adsb_swap(c, u, up)) return rc;
+            if (int rc = adsb_compute_rhs(c, &sub[s].form, up, u)) return rc;
+            if (sub[s].fix_axis >= 0) {
+                const int ax = sub[s].fix_axis;
+                if (ax >= c->ndim || sub[s].fix_buf < 0 || sub[s].fix_buf >= ADSB_MAX_BUFFERS || !c->buf[sub[s].fix_buf])
+                    return fail(ADSB_ESTATE, "step: bad fix_axis / fix_buf");
+                adsb_view v = local_view(c);
+                cudaError_t e = (cudaError_t) launch_set_plane(c->buf[u], v.s, v.n, ax, 0, c->buf[sub[s].fix_buf], c->stream);
+                if (e != cudaSuccess) return cuda_fail(e, "set_plane kernel");
+                c->launches++;
+            }
+            if (int rc = adsb_solve(c, u, sub[s].slots)) return rc;
+        }
+    }
+    return ADSB_OK;
+}
+
+int adsb_enable_timing(adsb_ctx* c, int on) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    c->timing = on != 0;
+    return ADSB_OK;
+}
+
+int adsb_stage_times(adsb_ctx* c, double* ms5) {
+    if (!c || !ms5) return fail(ADSB_EINVAL, "stage_times: null argument");
+    if (int rc = select_device(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& s : c->spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        c->acc_ms[s.stage] += ms;
+        c->free_events.push_back(s.a);
+        c->free_events.push_back(s.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < 5; ++i) {
+        ms5[i] = c->acc_ms[i];
+        c->acc_ms[i] = 0;
+    }
+    return ADSB_OK;
+}
+
+long long adsb_launch_count(adsb_ctx* c) { return c ? c->launches : 0; }
+
+static int quad_axes(adsb_ctx* c, QuadAxes& A) {
+    A = QuadAxes{};
+    A.ndim = c->ndim;
+    for (int d = 0; d < c->ndim; ++d) {
+        const AxisData& a = c->ax[d];
+        if (!a.tables) return fail(ADSB_ESTATE, "axis tables not uploaded");
+        A.p[d] = a.p;
+        A.q[d] = a.q;
+        A.ne[d] = a.elements;
+        A.st[d] = (a.ders + 1) * (a.p + 1);
+        A.bt[d] = a.d_bt;
+        A.xq[d] = a.d_xq;
+        A.w[d] = a.d_w;
+        A.J[d] = a.d_J;
+    }
+    return ADSB_OK;
+}
+
+int adsb_load_tensor(adsb_ctx* c, int source, int with_test_function, int dst) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    if (source != 1) return fail(ADSB_EINVAL, "load_tensor: unknown source");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, dst)) return rc;
+    QuadAxes A;
+    if (int rc = quad_axes(c, A)) return rc;
+    StageTimer t(c, 4);
+    if (with_test_function) {
+        cudaError_t e = (cudaError_t) launch_project(3, A, c->buf[dst], c->lo, c->cnt, c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "project kernel");
+        c->launches++;
+        return ADSB_OK;
+    }
+    int elo[3] = {0, 0, 0}, en[3] = {1, 1, 1};
+    size_t count = 1;
+    for (int d = 0; d < c->ndim; ++d) {
+        elo[d] = std::max(0, c->lo[d] - c->ax[d].p);
+        const int ehi = std::min(c->ax[d].elements - 1, c->lo[d] + c->cnt[d] - 1);
+        en[d] = ehi - elo[d] + 1;
+        count *= (size_t) en[d];
+    }
+    double* G = nullptr;
+    CU(cudaMalloc((void**) &G, count * sizeof(double)));
+    cudaError_t e = (cudaError_t) launch_element_source(3, A, G, elo, en, c->stream);
+    if (e == cudaSuccess) e = (cudaError_t) launch_box_sum(A, G, c->buf[dst], elo, en, c->lo, c->cnt, c->stream);
+    c->launches += 2;
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(G);
+    if (e != cudaSuccess) return cuda_fail(e, "load tensor kernels");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "load tensor kernels");
+    return ADSB_OK;
+}
+
+int adsb_project_init(adsb_ctx* c, int state, int dst) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    if (state < 0 || state > 2) return fail(ADSB_EINVAL, "project_init: unknown state");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, dst)) return rc;
+    QuadAxes A;
+    if (int rc = quad_axes(c, A)) return rc;
+    StageTimer t(c, 4);
+    cudaError_t e = (cudaError_t) launch_project(state, A, c->buf[dst], c->lo, c->cnt, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "project kernel");
+    c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int* dims, double* Lm,
+                    int* pv, double* Ut, double* rinv, double* Phi, double* Psi, double* T) {
+    SweepPlan P;
+    if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, P)) return rc;
+    const size_t rows = (size_t) P.S * P.CH;
+    if (dims) {
+        dims[0] = P.KL; dims[1] = P.KD; dims[2] = P.piv; dims[3] = P.CH; dims[4] = P.S; dims[5] = (int) rows;
+    }
+    auto put = [](auto* dst, const auto& v, size_t padded) {
+        if (!dst) return;
+        std::fill(dst, dst + padded, 0);
+        std::copy(v.begin(), v.end(), dst);
+    };
+    put(Lm, P.Lm, rows * P.KL);
+    put(pv, P.pv, rows);
+    put(Ut, P.Ut, rows * P.KD);
+    put(rinv, P.rinv, rows);
+    put(Phi, P.Phi, rows * P.KL);
+    put(Psi, P.Psi, rows * P.KD);
+    put(T, P.T, P.T.size());
+    return ADSB_OK;
+}
+
+}  // extern "C"

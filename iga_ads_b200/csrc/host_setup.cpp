@@ -1,0 +1,388 @@
+// host_setup.cpp -- the once-per-simulation host work of the ADS step, C++17, no CUDA.
+//
+// Written from scratch; numerically it follows the reference algorithms step for step so the
+// tables and factors that get uploaded are the ones the reference computes:
+//   Gauss rule            include/ads/quad/gauss.hpp:14-15 (hard-coded 20-digit literals there;
+//                         recomputed here in long double and rounded)
+//   knot vector / spans   src/ads/bspline/bspline.cpp:26-43, :61-81
+//   basis + derivatives   src/ads/bspline/bspline.cpp:102-160 (NURBS book A2.3)
+//   quadrature tables     src/ads/basis_data.cpp:63-114
+//   1-D matrices          src/ads/form_matrix.cpp:8-60, examples/implicit/implicit.hpp:46-64
+//   fix_dof               src/ads/simulation/dimension.cpp:23-29
+//   band LU               include/ads/lin/band_solve.hpp:16-18 -> LAPACK dgbtrf_ (unblocked DGBTF2
+//                         is what LAPACK runs for these bandwidths)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "adsb200.h"
+#include "internal.hpp"
+
+namespace adsb {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+namespace {
+
+inline double mix(double t, double a, double b) { return (1 - t) * a + t * b; }
+inline double mix(int i, int n, double a, double b) {
+    return mix(static_cast<double>(i) / static_cast<double>(n), a, b);
+}
+
+// Legendre P_q and its derivative at t
+void legendre(int q, long double t, long double& val, long double& der) {
+    long double pm = 1, pc = t;
+    for (int k = 2; k <= q; ++k) {
+        long double pn = ((2 * k - 1) * t * pc - (k - 1) * pm) / k;
+        pm = pc;
+        pc = pn;
+    }
+    val = pc;
+    der = q * (t * pc - pm) / (t * t - 1);
+}
+
+}  // namespace
+
+int gauss_rule(int q, double* x, double* w) {
+    if (q < 2 || q > 64) return fail(ADSB_EINVAL, "gauss: q must be in 2..64");
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int i = 0; i < q; ++i) {
+        long double t = cosl(pi * (i + 0.75L) / (q + 0.5L));  // i-th root from the right
+        long double v, d;
+        for (int it = 0; it < 100; ++it) {
+            legendre(q, t, v, d);
+            long double step = v / d;
+            t -= step;
+            if (fabsl(step) < 1e-21L) break;
+        }
+        if (2 * i + 1 == q) t = 0;
+        legendre(q, t, v, d);
+        x[q - 1 - i] = static_cast<double>(t);
+        w[q - 1 - i] = static_cast<double>(2 / ((1 - t * t) * d * d));
+    }
+    return ADSB_OK;
+}
+
+int make_knots(int p, int elements, double a, double b, double* knot) {
+    if (p < 1 || elements < 1) return fail(ADSB_EINVAL, "knots: need p >= 1, elements >= 1");
+    const int size = elements + 2 * p + 1;
+    for (int i = 0; i <= p; ++i) {
+        knot[i] = a;
+        knot[size - 1 - i] = b;
+    }
+    for (int i = 1; i < elements; ++i) knot[p + i] = mix(i, elements, a, b);
+    return size;
+}
+
+int find_span(double x, const double* knot, int knot_size, int p) {
+    int lo = p, hi = knot_size - p - 1;
+    if (x >= knot[hi]) return hi - 1;
+    if (x <= knot[lo]) return lo;
+    int mid = (lo + hi) / 2;
+    while (x < knot[mid] || x >= knot[mid + 1]) {
+        (x < knot[mid] ? hi : lo) = mid;
+        mid = (lo + hi) / 2;
+    }
+    return mid;
+}
+
+// out[d*(p+1) + r], d = 0..ders
+void basis_ders(int span, double x, const double* knot, int p, int ders, double* out) {
+    constexpr int M = ADSB_MAX_P + 2;
+    double ndu[M][M], a[2][M], left[M], right[M];
+    ndu[0][0] = 1;
+    for (int j = 1; j <= p; ++j) {
+        left[j] = x - knot[span + 1 - j];
+        right[j] = knot[span + j] - x;
+        double saved = 0;
+        for (int r = 0; r < j; ++r) {
+            ndu[j][r] = right[r + 1] + left[j - r];
+            double tmp = ndu[r][j - 1] / ndu[j][r];
+            ndu[r][j] = saved + right[r + 1] * tmp;
+            saved = left[j - r] * tmp;
+        }
+        ndu[j][j] = saved;
+    }
+    for (int j = 0; j <= p; ++j) out[j] = ndu[j][p];
+    for (int r = 0; r <= p; ++r) {
+        int s1 = 0, s2 = 1;
+        a[0][0] = 1;
+        for (int k = 1; k <= ders; ++k) {
+            double d = 0;
+            const int rk = r - k, pk = p - k;
+            if (r >= k) {
+                a[s2][0] = a[s1][0] / ndu[pk + 1][rk];
+                d = a[s2][0] * ndu[rk][pk];
+            }
+            const int j1 = rk >= -1 ? 1 : -rk;
+            const int j2 = r - 1 <= pk ? k - 1 : p - r;
+            for (int j = j1; j <= j2; ++j) {
+                a[s2][j] = (a[s1][j] - a[s1][j - 1]) / ndu[pk + 1][rk + j];
+                d += a[s2][j] * ndu[rk + j][pk];
+            }
+            if (r <= pk) {
+                a[s2][k] = -a[s1][k - 1] / ndu[pk + 1][r];
+                d += a[s2][k] * ndu[r][pk];
+            }
+            out[k * (p + 1) + r] = d;
+            std::swap(s1, s2);
+        }
+    }
+    int f = p;
+    for (int k = 1; k <= ders; ++k) {
+        for (int j = 0; j <= p; ++j) out[k * (p + 1) + j] *= f;
+        f *= (p - k);
+    }
+}
+
+int basis_tables(int p, int elements, double a, double b, int q, int ders, double* bt, double* xq,
+                 double* w, double* J, int* first_dof) {
+    if (p < 1 || p > ADSB_MAX_P) return fail(ADSB_EINVAL, "basis_tables: p out of range");
+    if (ders < 0 || ders > p) return fail(ADSB_EINVAL, "basis_tables: ders out of range");
+    if (elements < 1) return fail(ADSB_EINVAL, "basis_tables: elements < 1");
+    std::vector<double> knot(elements + 2 * p + 1), gx(q), gw(q);
+    int ks = make_knots(p, elements, a, b, knot.data());
+    if (ks < 0) return ks;
+    if (int rc = gauss_rule(q, gx.data(), gw.data())) return rc;
+    for (int k = 0; k < q; ++k) w[k] = gw[k];
+    // element end points are the distinct knots (elem_division = 1 => lerp(k, 1, x1, x2))
+    for (int e = 0; e < elements; ++e) {
+        // elem_division = 1: lerp(0, 1, x1, x2) == x1 and lerp(1, 1, x1, x2) == x2 exactly
+        const double x1 = knot[p + e], x2 = knot[p + e + 1];
+        J[e] = 0.5 * (x2 - x1);
+        first_dof[e] = e;
+        for (int k = 0; k < q; ++k) {
+            double t = 0.5 * (gx[k] + 1);
+            double xx = mix(t, x1, x2);
+            xq[e * q + k] = xx;
+            int span = find_span(xx, knot.data(), ks, p);
+            basis_ders(span, xx, knot.data(), p, ders,
+                       bt + (static_cast<size_t>(e) * q + k) * (ders + 1) * (p + 1));
+        }
+    }
+    return ADSB_OK;
+}
+
+// band layout helpers: A(i,j) at ab[j*ldab + kl+ku+i-j], kl = ku = p, ldab = 3p+1
+int matrix_from_tables(int kind, double h, int p, int elements, int q, int ders, const double* bt,
+                       const double* w, const double* J, double* ab) {
+    if ((kind == 1 || kind == 2 || kind == 3) && ders < 1)
+        return fail(ADSB_EINVAL, "matrix_1d: derivative tables needed");
+    const int n = elements + p, ldab = 3 * p + 1;
+    std::fill(ab, ab + static_cast<size_t>(ldab) * n, 0.0);
+    auto at = [&](int i, int j) -> double& { return ab[static_cast<size_t>(j) * ldab + 2 * p + i - j]; };
+    const int m = p + 1;
+    for (int e = 0; e < elements; ++e) {
+        for (int k = 0; k < q; ++k) {
+            const double* val = bt + (static_cast<size_t>(e) * q + k) * (ders + 1) * m;
+            const double* der = ders >= 1 ? val + m : nullptr;
+            for (int r = 0; r < m; ++r) {
+                for (int c = 0; c < m; ++c) {
+                    double& dst = at(e + r, e + c);
+                    switch (kind) {
+                    case 0: dst += val[r] * val[c] * w[k] * J[e]; break;
+                    case 1: dst += der[r] * der[c] * w[k] * J[e]; break;
+                    case 2: dst += val[r] * der[c] * w[k] * J[e]; break;
+                    default: dst += (val[r] * val[c] + h * der[r] * der[c]) * w[k] * J[e]; break;
+                    }
+                }
+            }
+        }
+    }
+    return ADSB_OK;
+}
+
+void fix_dof(int k, int p, int n, double* ab) {
+    const int ldab = 3 * p + 1, last = n - 1;
+    auto at = [&](int i, int j) -> double& { return ab[static_cast<size_t>(j) * ldab + 2 * p + i - j]; };
+    for (int i = std::max(k - p, 0); i <= std::min(k + p, last); ++i) at(k, i) = 0;
+    at(k, k) = 1;
+}
+
+int matrix_1d(int kind, int p, int elements, double a, double b, double h, int fix, double* ab) {
+    if (kind < 0 || kind > 3) return fail(ADSB_EINVAL, "matrix_1d: kind must be 0..3");
+    if (p < 1 || p > ADSB_MAX_P || elements < 1) return fail(ADSB_EINVAL, "matrix_1d: bad p/elements");
+    const int q = p + 1, ders = 1, m = p + 1;
+    std::vector<double> bt(static_cast<size_t>(elements) * q * (ders + 1) * m), xq(elements * q), w(q),
+        J(elements);
+    std::vector<int> fd(elements);
+    if (int rc = basis_tables(p, elements, a, b, q, ders, bt.data(), xq.data(), w.data(), J.data(), fd.data()))
+        return rc;
+    if (int rc = matrix_from_tables(kind, h, p, elements, q, ders, bt.data(), w.data(), J.data(), ab))
+        return rc;
+    if (fix & 1) fix_dof(0, p, elements + p, ab);
+    if (fix & 2) fix_dof(elements + p - 1, p, elements + p, ab);
+    return ADSB_OK;
+}
+
+// Unblocked banded LU with partial pivoting on the LAPACK layout (DGBTF2 semantics).
+int band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv) {
+    if (n < 1 || kl < 0 || ku < 0 || ldab < 2 * kl + ku + 1)
+        return fail(ADSB_EINVAL, "band_factorize: bad dimensions");
+    const int kv = kl + ku;
+    auto A = [&](int r, int c) -> double& { return ab[static_cast<size_t>(c) * ldab + r]; };
+    for (int j = ku + 1; j < std::min(kv, n); ++j)
+        for (int i = kv - j; i < kl; ++i) A(i, j) = 0;
+    int ju = 0, info = 0;
+    for (int j = 0; j < n; ++j) {
+        if (j + kv < n)
+            for (int i = 0; i < kl; ++i) A(i, j + kv) = 0;
+        const int km = std::min(kl, n - 1 - j);
+        int jp = 0;
+        double best = std::fabs(A(kv, j));
+        for (int i = 1; i <= km; ++i) {
+            double v = std::fabs(A(kv + i, j));
+            if (v > best) {
+                best = v;
+                jp = i;
+            }
+        }
+        ipiv[j] = j + jp + 1;
+        if (A(kv + jp, j) != 0) {
+            ju = std::max(ju, std::min(j + ku + jp, n - 1));
+            if (jp != 0)
+                for (int c = j; c <= ju; ++c) std::swap(A(kv + jp - (c - j), c), A(kv - (c - j), c));
+            if (km > 0) {
+                const double r = 1.0 / A(kv, j);
+                for (int i = 1; i <= km; ++i) A(kv + i, j) *= r;
+                for (int c = j + 1; c <= ju; ++c) {
+                    const double t = A(kv - (c - j), c);
+                    if (t != 0)
+                        for (int i = 1; i <= km; ++i) A(kv + i - (c - j), c) -= A(kv + i, j) * t;
+                }
+            }
+        } else if (info == 0) {
+            info = j + 1;
+        }
+    }
+    if (info) return fail(ADSB_ESINGULAR, "band_factorize: zero pivot at column " + std::to_string(info));
+    return ADSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plan for the chunk-parallel substitution kernel (kernels_sweep.cu).  A line of n unknowns is cut
+// into S chunks of CH columns.  Each chunk runs the forward / backward recurrences from a zero
+// incoming state; the exact result is recovered as local + (homogeneous response) * (true
+// incoming state), where the states are chained by a short scan over chunks.  All homogeneous
+// responses depend only on the factor, so they are tabulated here once.
+// ---------------------------------------------------------------------------------------------
+int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch,
+                     SweepPlan& P) {
+    const int kd = kl + ku;
+    bool piv = false;
+    for (int j = 0; j < n; ++j) {
+        int t = ipiv[j] - 1 - j;
+        if (t < 0 || t > kl || j + t >= n) return fail(ADSB_EINVAL, "factor: bad pivot vector");
+        if (t) piv = true;
+    }
+    auto Aat = [&](int r, int c) { return ab[static_cast<size_t>(c) * ldab + r]; };
+    int kd_eff = 0;  // widest non-zero super-diagonal of U
+    for (int c = 0; c < n; ++c)
+        for (int k = 1; k <= std::min(kd, c); ++k)
+            if (Aat(kd - k, c) != 0) kd_eff = std::max(kd_eff, k);
+    for (int j = 0; j < n; ++j)
+        if (Aat(kd, j) == 0) return fail(ADSB_ESINGULAR, "factor: zero diagonal in U at column " + std::to_string(j + 1));
+    // template variant: (KL, KD) = (P, P) without pivoting, (P, 2P) with
+    int var = piv ? std::max({kl, (kd_eff + 1) / 2, 1}) : std::max({kl, kd_eff, 1});
+    if (var > 5) return fail(ADSB_EINVAL, "factor: bandwidth beyond the compiled kernel variants (p <= 5)");
+    const int KL = var, KD = piv ? 2 * var : var;
+    P.n = n; P.KL = KL; P.KD = KD; P.piv = piv ? 1 : 0; P.CH = ch;
+    const int S = (n + ch - 1) / ch;
+    P.S = S;
+    P.Lm.assign(static_cast<size_t>(n) * KL, 0.0);
+    P.pv.assign(n, 0);
+    P.Ut.assign(static_cast<size_t>(n) * KD, 0.0);
+    P.rinv.assign(n, 0.0);
+    P.Phi.assign(static_cast<size_t>(n) * KL, 0.0);
+    P.Psi.assign(static_cast<size_t>(n) * KD, 0.0);
+    P.T.assign(static_cast<size_t>(S) * KL * KL, 0.0);
+    for (int j = 0; j < n; ++j) {
+        const int lm = std::min(kl, n - 1 - j);
+        for (int i = 0; i < lm; ++i) P.Lm[static_cast<size_t>(j) * KL + i] = Aat(kd + 1 + i, j);
+        P.pv[j] = ipiv[j] - 1 - j;
+        for (int k = 1; k <= kd_eff && j + k < n; ++k) P.Ut[static_cast<size_t>(j) * KD + k - 1] = Aat(kd - k, j + k);
+        P.rinv[j] = 1.0 / Aat(kd, j);
+    }
+    // forward responses: unit perturbation of window row r at the chunk start, zero data after it
+    std::vector<double> win(ch + KL);
+    for (int s = 0; s < S; ++s) {
+        const int j0 = s * ch;
+        for (int r = 0; r < KL; ++r) {
+            std::fill(win.begin(), win.end(), 0.0);
+            win[r] = 1.0;
+            for (int i = 0; i < ch && j0 + i < n; ++i) {
+                const int j = j0 + i;
+                const int t = P.pv[j];
+                if (t) std::swap(win[i], win[i + t]);
+                for (int m = 1; m <= KL; ++m) win[i + m] = std::fma(-P.Lm[static_cast<size_t>(j) * KL + m - 1], win[i], win[i + m]);
+                P.Phi[static_cast<size_t>(j) * KL + r] = win[i];
+            }
+            if (j0 + ch <= n)
+                for (int m = 0; m < KL; ++m) P.T[(static_cast<size_t>(s) * KL + m) * KL + r] = win[ch + m];
+        }
+    }
+    // backward responses: unit value of the k-th unknown right of the chunk, zero data
+    std::vector<double> xs(ch + KD);
+    for (int s = 0; s < S; ++s) {
+        const int j0 = s * ch;
+        for (int k = 0; k < KD; ++k) {
+            std::fill(xs.begin(), xs.end(), 0.0);
+            xs[ch + k] = 1.0;
+            for (int i = ch - 1; i >= 0; --i) {
+                const int j = j0 + i;
+                if (j >= n) continue;
+                double acc = 0;
+                for (int m = KD; m >= 1; --m) acc = std::fma(-P.Ut[static_cast<size_t>(j) * KD + m - 1], xs[i + m], acc);
+                xs[i] = acc * P.rinv[j];
+                P.Psi[static_cast<size_t>(j) * KD + k] = xs[i];
+            }
+        }
+    }
+    return ADSB_OK;
+}
+
+}  // namespace adsb
+
+// ------------------------------------- C ABI (host part) --------------------------------------
+extern "C" {
+
+int adsb_abi_version(void) { return ADSB_ABI_VERSION; }
+const char* adsb_last_error(void) { return adsb::g_last_error.c_str(); }
+
+int adsb_gauss(int q, double* x, double* w) { return adsb::gauss_rule(q, x, w); }
+
+int adsb_knots(int p, int elements, double a, double b, double* knots) {
+    return adsb::make_knots(p, elements, a, b, knots);
+}
+
+int adsb_find_span(double x, const double* knots, int knot_size, int p) {
+    return adsb::find_span(x, knots, knot_size, p);
+}
+
+int adsb_basis_ders(int span, double x, const double* knots, int p, int ders, double* out) {
+    if (p < 1 || p > ADSB_MAX_P || ders < 0) return adsb::fail(ADSB_EINVAL, "basis_ders: bad p/ders");
+    adsb::basis_ders(span, x, knots, p, ders, out);
+    return ADSB_OK;
+}
+
+int adsb_basis_tables(int p, int elements, double a, double b, int q, int ders, double* b_flat,
+                      double* xq, double* w, double* J, int* first_dof) {
+    return adsb::basis_tables(p, elements, a, b, q, ders, b_flat, xq, w, J, first_dof);
+}
+
+int adsb_matrix_1d(int kind, int p, int elements, double a, double b, double h, int fix, double* ab) {
+    return adsb::matrix_1d(kind, p, elements, a, b, h, fix, ab);
+}
+
+int adsb_band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv) {
+    return adsb::band_factorize(n, kl, ku, ab, ldab, ipiv);
+}
+
+}  // extern "C"

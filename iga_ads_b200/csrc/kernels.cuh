@@ -1,0 +1,84 @@
+// kernels.cuh -- device-side argument blocks and launcher prototypes (internal to libadsb200.so).
+#ifndef ADSB_KERNELS_CUH
+#define ADSB_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+namespace adsb {
+
+constexpr int SWEEP_CH = 33;  // columns per chunk held in registers by one thread
+
+// One factorised band matrix, prepared by build_sweep_plan (host_setup.cpp); rows padded to S*CH.
+struct SweepFactor {
+    const double* Lm;    // [S*CH][KL]
+    const int* pv;       // [S*CH]
+    const double* Ut;    // [S*CH][KD]
+    const double* rinv;  // [S*CH]
+    const double* Phi;   // [S*CH][KL]
+    const double* Psi;   // [S*CH][KD]
+    const double* T;     // [S][KL][KL]
+    int n, S, KL, KD, piv;
+};
+
+// Lines of one sweep.  A line is addressed as base(l0, l1) + off(j):
+//   base = l0*s0 + l1*s1, off(j) = off[j] if off != nullptr else j*sj.
+// STRIDED mode wants s0 == 1 (lanes run along l0); CONTIG mode wants sj == 1.
+struct SweepGeom {
+    const double* in;
+    double* out;
+    const long long* off_in;
+    const long long* off_out;
+    long long sj_in, sj_out;
+    long long s0_in, s0_out;
+    long long s1_in, s1_out;
+    int L0, L1;
+    int pitch;  // CONTIG: shared-memory row pitch in doubles (odd)
+};
+
+// returns cudaError_t as int
+int launch_sweep(const SweepFactor& F, const SweepGeom& G, bool contig, int NL, cudaStream_t st);
+int sweep_smem_bytes(const SweepFactor& F, bool contig, int NL, int pitch);
+
+// Collapsed right-hand side: rhs = sum over Kronecker terms of 1-D band operators applied to u.
+// op[d] points at coefficient rows [n_d][2p+1] (row i holds A(i, i-p .. i+p), zero outside).
+struct RhsOps {
+    const double* Mx;  // Gram
+    const double* Sx;  // stiffness
+    const double* My;
+    const double* Sy;
+    const double* Mz;
+    const double* Sz;
+    int p[3];
+    int n[3];  // global extents
+};
+struct RhsGeom {
+    const double* in;
+    double* out;
+    const double* forcing;  // same layout as out, or nullptr
+    long long si[3], so[3];
+    int in_lo[3], in_n[3];    // box covered by `in` in global indices
+    int out_lo[3], out_n[3];  // box to produce
+    double alpha, beta[3], gamma;
+};
+int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStream_t st);
+
+// Per-axis quadrature tables on the device (layout of adsb_basis_tables, ders = 1).
+struct QuadAxes {
+    int ndim;
+    int p[3], q[3], ne[3], st[3];  // st = (ders+1)*(p+1) doubles per quadrature point
+    const double* bt[3];  // [ne][q][2][p+1]
+    const double* xq[3];  // [ne][q]
+    const double* w[3];   // [q]
+    const double* J[3];   // [ne]
+};
+int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], const int n[3], cudaStream_t st);
+int launch_element_source(int src, const QuadAxes& A, double* G, const int elo[3], const int en[3], cudaStream_t st);
+int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int elo[3], const int en[3],
+                   const int lo[3], const int n[3], cudaStream_t st);
+
+int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,
+                     const double* values, cudaStream_t st);
+
+}  // namespace adsb
+
+#endif

@@ -1,0 +1,378 @@
+"""Device context + the simulation layer of the reference, mirrored on top of the C ABI.
+
+    Context                     adsb_ctx (include/adsb200.h)
+    simulation_2d / _3d         include/ads/simulation/simulation_2d.hpp, simulation_3d.hpp:23-150
+                                 (x, y, z dimensions, shape(), prepare_matrices(), solve())
+    heat_3d, heat_2d,           examples/heat/heat_3d.hpp, heat_2d.hpp
+    implicit_2d, implicit_3d,   examples/implicit/implicit.hpp (+ its 3-axis extension)
+    scalability_2d/_3d          examples/scalability/test2d.hpp, test3d.hpp
+
+The coefficient tensors live on the GPU (managed buffers U, U_PREV, ...); `u` is downloaded only
+when the caller asks.  There is no CPU path: constructing a Context without a CUDA device raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import Form, Substep, View, check, d_, i_
+from .host import band_factorize, dimension, dim_config, timesteps_config  # noqa: F401
+
+U, U_PREV, FORCING, FIXROW, SCRATCH = 0, 1, 2, 3, 4
+
+
+class Context:
+    def __init__(self, n_global, lo=None, cnt=None, device=0):
+        self.lib = _lib.load()
+        self.ndim = len(n_global)
+        self.n_global = tuple(int(v) for v in n_global)
+        self.lo = tuple(lo) if lo is not None else (0,) * self.ndim
+        self.cnt = tuple(cnt) if cnt is not None else self.n_global
+        ng = np.array(self.n_global, dtype=np.int32)
+        lo_a = np.array(self.lo, dtype=np.int32)
+        cn = np.array(self.cnt, dtype=np.int32)
+        h = ctypes.c_void_p()
+        check(self.lib.adsb_create(self.ndim, i_(ng), i_(lo_a), i_(cn), device, ctypes.byref(h)))
+        self.h = h
+        self.local_size = int(np.prod(self.cnt))
+
+    def close(self):
+        if self.h:
+            self.lib.adsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup
+    def set_stream(self, stream_ptr):
+        check(self.lib.adsb_set_stream(self.h, ctypes.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        check(self.lib.adsb_synchronize(self.h))
+
+    def set_axis(self, axis, dim):
+        t = dim.basis
+        check(self.lib.adsb_set_axis_tables(self.h, axis, dim.p, dim.elements, dim.quad_order,
+                                            dim.derivatives, d_(t["b"]), d_(t["x"]), d_(t["w"]),
+                                            d_(t["J"]), i_(t["first_dof"])))
+
+    def set_factor(self, axis, slot, lu, ipiv, kl, ku):
+        lu = np.ascontiguousarray(lu, dtype=np.float64)
+        ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+        check(self.lib.adsb_set_axis_factor(self.h, axis, slot, lu.shape[0], kl, ku, lu.shape[1],
+                                            d_(lu), i_(ipiv)))
+
+    # ---- tensors
+    def upload(self, buf, host):
+        a = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        assert a.size == self.local_size
+        check(self.lib.adsb_upload(self.h, buf, d_(a)))
+
+    def download(self, buf):
+        out = np.empty(self.local_size)
+        check(self.lib.adsb_download(self.h, buf, d_(out)))
+        return out
+
+    def swap(self, a, b):
+        check(self.lib.adsb_swap(self.h, a, b))
+
+    def zero(self, buf):
+        check(self.lib.adsb_zero(self.h, buf))
+
+    def bind(self, buf, device_ptr):
+        check(self.lib.adsb_bind(self.h, buf, ctypes.c_void_p(device_ptr)))
+
+    def device_ptr(self, buf):
+        p = self.lib.adsb_device_ptr(self.h, buf)
+        if not p:
+            raise _lib.AdsbError(-5, self.lib.adsb_last_error().decode())
+        return p
+
+    def set_plane(self, buf, axis, idx, values):
+        v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        check(self.lib.adsb_set_plane(self.h, buf, axis, idx, d_(v)))
+
+    # ---- the hot path
+    def compute_rhs(self, form, src, dst):
+        check(self.lib.adsb_compute_rhs(self.h, ctypes.byref(form), src, dst))
+
+    def load_tensor(self, source, with_test_function, dst):
+        check(self.lib.adsb_load_tensor(self.h, source, int(with_test_function), dst))
+
+    def project_init(self, state, dst):
+        check(self.lib.adsb_project_init(self.h, state, dst))
+
+    def solve(self, buf, slots=None):
+        s = np.array(list(slots or ()) + [0] * (3 - len(slots or ())), dtype=np.int32)
+        check(self.lib.adsb_solve(self.h, buf, i_(s)))
+
+    def sweep(self, buf, axis, slot=0):
+        check(self.lib.adsb_sweep(self.h, buf, axis, slot))
+
+    def step(self, substeps, nsteps, u=U, u_prev=U_PREV):
+        arr = (Substep * len(substeps))(*substeps)
+        check(self.lib.adsb_step(self.h, u, u_prev, arr, len(substeps), nsteps))
+
+    def sweep_view(self, axis, slot, in_ptr, vin, out_ptr, vout, off_in=None, off_out=None):
+        oi = np.ascontiguousarray(off_in, dtype=np.int64) if off_in is not None else None
+        oo = np.ascontiguousarray(off_out, dtype=np.int64) if off_out is not None else None
+        check(self.lib.adsb_sweep_view(
+            self.h, axis, slot, ctypes.c_void_p(in_ptr), ctypes.byref(vin),
+            oi.ctypes.data_as(_lib.llp) if oi is not None else None,
+            ctypes.c_void_p(out_ptr), ctypes.byref(vout),
+            oo.ctypes.data_as(_lib.llp) if oo is not None else None))
+
+    def rhs_view(self, form, in_ptr, vin, in_lo, out_ptr, vout, out_lo, forcing_ptr=None):
+        il = np.array(list(in_lo) + [0] * (3 - len(in_lo)), dtype=np.int32)
+        ol = np.array(list(out_lo) + [0] * (3 - len(out_lo)), dtype=np.int32)
+        check(self.lib.adsb_rhs_view(self.h, ctypes.byref(form), ctypes.c_void_p(in_ptr), ctypes.byref(vin),
+                                     i_(il), ctypes.c_void_p(forcing_ptr) if forcing_ptr else None,
+                                     ctypes.c_void_p(out_ptr), ctypes.byref(vout), i_(ol)))
+
+    # ---- measurement
+    def enable_timing(self, on=True):
+        check(self.lib.adsb_enable_timing(self.h, int(on)))
+
+    def stage_times(self):
+        ms = np.zeros(5)
+        check(self.lib.adsb_stage_times(self.h, d_(ms)))
+        return dict(rhs=ms[0], sweep_x=ms[1], sweep_y=ms[2], sweep_z=ms[3], other=ms[4])
+
+    def launch_count(self):
+        return int(self.lib.adsb_launch_count(self.h))
+
+
+class _simulation:
+    """Common part of simulation_2d / simulation_3d: dimensions, shape(), prepare_matrices(), solve()."""
+
+    def __init__(self, dims, steps, device=0):
+        self.dims = list(dims)
+        self.steps = steps
+        self.device = device
+        self.ctx = None
+
+    def shape(self):
+        return tuple(d.dofs() for d in self.dims)
+
+    def _context(self):
+        if self.ctx is None:
+            self.ctx = Context(self.shape(), device=self.device)
+            for ax, d in enumerate(self.dims):
+                self.ctx.set_axis(ax, d)
+        return self.ctx
+
+    def prepare_matrices(self):
+        """x.factorize_matrix(); y...; (simulation_3d.hpp:58-62) + upload of the factors to slot 0."""
+        ctx = self._context()
+        for ax, d in enumerate(self.dims):
+            lu, ipiv = d.factorize_matrix()
+            ctx.set_factor(ax, 0, lu, ipiv, d.p, d.p)
+
+    def add_factor(self, axis, slot, ab):
+        """Factorise another matrix of this axis (K = M + h S ...) into `slot`."""
+        d = self.dims[axis]
+        lu, ipiv = band_factorize(ab, d.p, d.p)
+        self._context().set_factor(axis, slot, lu, ipiv, d.p, d.p)
+
+    def solve(self, buf=U, slots=None):
+        self._context().solve(buf, slots)
+
+    # simulation_base::run (src/ads/simulation/simulation_base.cpp:11-20)
+    def run(self):
+        self.before()
+        self.advance(self.steps.step_count)
+        self.after()
+
+    def before(self):
+        pass
+
+    def after(self):
+        pass
+
+    def set_state(self, u):
+        self._context().upload(U, u)
+
+    def state(self):
+        return self._context().download(U)
+
+    def advance(self, nsteps):
+        self._context().step(self.substeps(), nsteps)
+
+    def substeps(self):
+        raise NotImplementedError
+
+
+class simulation_2d(_simulation):
+    def __init__(self, config_x, config_y, steps, derivatives=1, device=0):
+        super().__init__([dimension(config_x, derivatives), dimension(config_y, derivatives)], steps, device)
+        self.x, self.y = self.dims
+
+
+class simulation_3d(_simulation):
+    def __init__(self, config_x, config_y, config_z, steps, derivatives=1, device=0):
+        super().__init__([dimension(c, derivatives) for c in (config_x, config_y, config_z)], steps, device)
+        self.x, self.y, self.z = self.dims
+
+
+# ------------------------------------------------------------------------------------ problems
+class heat_3d(simulation_3d):
+    """examples/heat/heat_3d.hpp: rhs = (u,v) - dt (grad u, grad v); solve with Mx (x) My (x) Mz."""
+
+    def __init__(self, p, elements, steps, method=_lib.RHS_COLLAPSED, device=0):
+        c = dim_config(p, elements)
+        super().__init__(c, c, c, steps, device=device)
+        self.method = method
+
+    def before(self):
+        self.prepare_matrices()
+        self._context().project_init(0, U)
+        self.solve(U)
+
+    def substeps(self):
+        dt = self.steps.dt
+        return [Substep.make(Form.make(1.0, (dt, dt, dt), method=self.method))]
+
+
+class heat_2d(simulation_2d):
+    """examples/heat/heat_2d.hpp: x.fix_left(); row x=0 of the rhs is overwritten with the 1-D
+    projection of sin(pi y) before every solve (heat_2d.hpp:40-52)."""
+
+    def __init__(self, p, elements, steps, method=_lib.RHS_COLLAPSED, device=0):
+        c = dim_config(p, elements)
+        super().__init__(c, c, steps, device=device)
+        self.method = method
+
+    def prepare_matrices(self):
+        self.x.fix_left()
+        super().prepare_matrices()
+        row = self.dirichlet_row()
+        padded = np.zeros(self._context().local_size)
+        padded[:row.size] = row
+        self._context().upload(FIXROW, padded)
+
+    def dirichlet_row(self):
+        """compute_projection(buf, y.basis, sin(pi y)) (include/ads/projection.hpp:12-36), host, O(n)."""
+        t = self.y.basis
+        ne, q, p = self.y.elements, self.y.quad_order, self.y.p
+        buf = np.zeros(self.y.dofs())
+        for e in range(ne):
+            for k in range(q):
+                wj = t["w"][k] * t["J"][e]
+                fx = np.sin(t["x"][e, k] * np.pi)
+                for a in range(p + 1):
+                    buf[e + a] += fx * t["b"][e, k, 0, a] * wj
+        return buf
+
+    def before(self):
+        self.prepare_matrices()
+        ctx = self._context()
+        ctx.zero(U)  # init_state == 0 (heat_2d.hpp:32-38)
+        ctx.set_plane(U, 0, 0, self.dirichlet_row())
+        self.solve(U)
+
+    def substeps(self):
+        dt = self.steps.dt
+        return [Substep.make(Form.make(1.0, (dt, dt), method=self.method), fix_axis=0, fix_buf=FIXROW)]
+
+
+class implicit_2d(simulation_2d):
+    """examples/implicit/implicit.hpp: two half steps, K = M + dt/2 S implicit along one axis."""
+
+    def __init__(self, p, elements, steps, method=_lib.RHS_COLLAPSED, device=0):
+        c = dim_config(p, elements)
+        super().__init__(c, c, steps, device=device)
+        self.method = method
+
+    def prepare_matrices(self):
+        super().prepare_matrices()
+        h = 0.5 * self.steps.dt
+        self.add_factor(0, 1, self.x.matrix(3, h))
+        self.add_factor(1, 1, self.y.matrix(3, h))
+
+    def before(self):
+        self.prepare_matrices()
+        self._context().project_init(1, U)
+        self.solve(U)
+
+    def substeps(self):
+        h = 0.5 * self.steps.dt
+        return [Substep.make(Form.make(1.0, (0.0, h), method=self.method), slots=(1, 0)),
+                Substep.make(Form.make(1.0, (h, 0.0), method=self.method), slots=(0, 1))]
+
+
+class implicit_3d(simulation_3d):
+    """3-axis extension of implicit_2d (oracle/ref_driver.cpp implicit_3d_ref):
+    sub-step d is implicit along axis d with K_d = M_d + (dt/3) S_d."""
+
+    def __init__(self, p, elements, steps, method=_lib.RHS_COLLAPSED, device=0):
+        c = dim_config(p, elements)
+        super().__init__(c, c, c, steps, device=device)
+        self.method = method
+
+    def prepare_matrices(self):
+        super().prepare_matrices()
+        tau = self.steps.dt / 3.0
+        for ax, d in enumerate(self.dims):
+            self.add_factor(ax, 1, d.matrix(3, tau))
+
+    def before(self):
+        self.prepare_matrices()
+        self._context().project_init(1, U)
+        self.solve(U)
+
+    def substeps(self):
+        tau = self.steps.dt / 3.0
+        out = []
+        for d in range(3):
+            beta = [tau] * 3
+            beta[d] = 0.0
+            slots = [0] * 3
+            slots[d] = 1
+            out.append(Substep.make(Form.make(1.0, beta, method=self.method), slots=slots))
+        return out
+
+
+class _scalability:
+    def prepare_matrices(self):
+        self.x.fix_left()
+        super().prepare_matrices()
+        # time-independent load: dt * sum_q f(x_q) w J added to every DOF of the element
+        self._context().load_tensor(1, False, FORCING)
+
+    def before(self):
+        self.prepare_matrices()
+        ctx = self._context()
+        ctx.upload(U, np.ones(ctx.local_size))
+        self.solve(U)
+
+    def substeps(self):
+        dt = self.steps.dt
+        beta = (dt,) * len(self.dims)
+        return [Substep.make(Form.make(1.0, beta, gamma=dt, forcing_buf=FORCING, method=self.method))]
+
+
+class scalability_3d(_scalability, simulation_3d):
+    """examples/scalability/test3d.hpp"""
+
+    def __init__(self, p, elements, steps, method=_lib.RHS_COLLAPSED, device=0):
+        c = dim_config(p, elements)
+        simulation_3d.__init__(self, c, c, c, steps, device=device)
+        self.method = method
+
+
+class scalability_2d(_scalability, simulation_2d):
+    """examples/scalability/test2d.hpp"""
+
+    def __init__(self, p, elements, steps, method=_lib.RHS_COLLAPSED, device=0):
+        c = dim_config(p, elements)
+        simulation_2d.__init__(self, c, c, steps, device=device)
+        self.method = method
+
+
+PROBLEMS = {"heat_3d": heat_3d, "heat_2d": heat_2d, "implicit_2d": implicit_2d,
+            "implicit_3d": implicit_3d, "scalability_3d": scalability_3d,
+            "scalability_2d": scalability_2d}

@@ -1,0 +1,215 @@
+/* adsb200.h -- C ABI of libadsb200.so: the B200-native ADS time-step hot path.
+ *
+ * The reference (marcinlos/iga-ads) has no FFI boundary for this path: it is a C++17 template
+ * library whose "interface" is the class surface the examples inherit from, plus three LAPACK
+ * symbols.  This header is the boundary a maintainer would bind instead; each entry point cites
+ * the reference interface it replaces (paths relative to the reference tree).  The C++17 host
+ * layer in iga_ads_b200/include/ads/ (same names as the reference: ads::dimension,
+ * ads::simulation_2d/3d, ads::lin::tensor, ads::ads_solve ...) and the Python mirror in
+ * iga_ads_b200/ call nothing but these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; opaque handle adsb_ctx; no C++/torch types
+ *   - every function returns 0 on success, a negative code on failure, with a message in
+ *     adsb_last_error() (thread-local).  The reference ignores LAPACK `info`
+ *     (include/ads/lin/band_solve.hpp:17,:29); we surface it (singular factor => ADSB_ESINGULAR).
+ *   - tensors are column-major (first index fastest), exactly as ads::lin::tensor
+ *     (include/ads/util/multi_array/ordering/reverse.hpp:28-31)
+ *   - band matrices use the LAPACK general-band layout with factor workspace of
+ *     ads::lin::band_matrix(kl, ku, n): ldab = 2*kl+ku+1, A(i,j) at ab[j*ldab + kl+ku+i-j]
+ *     (include/ads/lin/band_matrix.hpp:31-40,:69-73)
+ *   - there is NO CPU fallback: device entry points fail with ADSB_ENODEVICE without a GPU.
+ */
+#ifndef ADSB200_H
+#define ADSB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADSB_ABI_VERSION 1
+
+#define ADSB_OK 0
+#define ADSB_EINVAL (-1)     /* bad argument */
+#define ADSB_ENODEVICE (-2)  /* no CUDA device / CUDA call failed */
+#define ADSB_ESINGULAR (-3)  /* zero pivot in a band factor (LAPACK info > 0) */
+#define ADSB_ESTATE (-4)     /* tables / factors / buffers not set up for this call */
+#define ADSB_ENOMEM (-5)
+
+#define ADSB_MAX_P 7         /* spline degree limit of the device kernels */
+#define ADSB_MAX_SLOTS 4     /* factor slots per axis (M, K, ...) */
+#define ADSB_MAX_BUFFERS 8   /* managed coefficient tensors per context */
+
+typedef struct adsb_ctx adsb_ctx;
+
+int adsb_abi_version(void);
+const char* adsb_last_error(void);
+
+/* ======================= host-side setup (pure CPU, O(n p^2 q)) ===========================
+ * Runs once per simulation; stays on the host exactly as in the reference. */
+
+/* Gauss-Legendre nodes (ascending) and weights on [-1,1], 2 <= q <= 64.
+ * Replaces quad::gauss::Xs/Ws (include/ads/quad/gauss.hpp:14-15). */
+int adsb_gauss(int q, double* x, double* w);
+
+/* Clamped uniform knot vector; returns its size elements+2p+1 (or <0).
+ * Replaces bspline::create_basis (src/ads/bspline/bspline.cpp:26-43, repeated_nodes = 0). */
+int adsb_knots(int p, int elements, double a, double b, double* knots);
+
+/* Replaces bspline::find_span (src/ads/bspline/bspline.cpp:61-81); returns the span. */
+int adsb_find_span(double x, const double* knots, int knot_size, int p);
+
+/* Values and derivatives of the p+1 non-zero B-splines at x: out[d*(p+1)+i], d = 0..ders.
+ * Replaces bspline::eval_basis_with_derivatives (src/ads/bspline/bspline.cpp:102-160). */
+int adsb_basis_ders(int span, double x, const double* knots, int p, int ders, double* out);
+
+/* Per-axis quadrature tables, flat: b[e][k][d][i] (elements x q x (ders+1) x (p+1)), xq[e][k],
+ * w[k], J[e], first_dof[e].  Replaces ads::basis_data (src/ads/basis_data.cpp:63-114). */
+int adsb_basis_tables(int p, int elements, double a, double b, int q, int ders, double* b_flat,
+                      double* xq, double* w, double* J, int* first_dof);
+
+/* 1-D quadrature matrices in band layout (ldab = 3p+1, n = elements+p columns), accumulated in
+ * the reference's loop order.  kind: 0 Gram, 1 stiffness, 2 advection
+ * (src/ads/form_matrix.cpp:8-60), 3 Gram + h*stiffness (examples/implicit/implicit.hpp:46-64,
+ * the caller passes the already scaled h).  fix: bit0 fix_left, bit1 fix_right
+ * (src/ads/simulation/dimension.cpp:23-29). */
+int adsb_matrix_1d(int kind, int p, int elements, double a, double b, double h, int fix,
+                   double* ab);
+
+/* Banded LU with partial pivoting, in place, 1-based ipiv.  Replaces lin::factorize -> dgbtrf_
+ * (include/ads/lin/band_solve.hpp:16-18).  Returns ADSB_ESINGULAR for an exactly zero pivot. */
+int adsb_band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv);
+
+/* ================================ device context ===========================================
+ * One context per GPU (one process per GPU).  It owns the device copies of the per-axis tables,
+ * operators and factors, and (optionally) managed coefficient tensors.
+ *
+ * n_global[d] are the DOF counts of the whole problem; lo[d]/cnt[d] the box this context owns
+ * (lo = 0, cnt = n_global for a single GPU; a z-slab or y-slab for a sharded run).  ndim 2 or 3. */
+int adsb_create(int ndim, const int* n_global, const int* lo, const int* cnt, int device,
+                adsb_ctx** out);
+int adsb_destroy(adsb_ctx* ctx);
+
+/* CUDA stream (cudaStream_t passed as void*) all later calls enqueue on; NULL = default stream. */
+int adsb_set_stream(adsb_ctx* ctx, void* cuda_stream);
+int adsb_synchronize(adsb_ctx* ctx);
+
+/* Upload one axis' quadrature tables (layout of adsb_basis_tables); the library derives the 1-D
+ * Gram / stiffness / advection operators from them by the same quadrature.
+ * Replaces the basis_data member of ads::dimension (include/ads/simulation/dimension.hpp:20-59)
+ * as seen by eval_basis / eval_fun (include/ads/simulation/simulation_3d.hpp:98-128). */
+int adsb_set_axis_tables(adsb_ctx* ctx, int axis, int p, int elements, int q, int ders,
+                         const double* b_flat, const double* xq, const double* w, const double* J,
+                         const int* first_dof);
+
+/* Upload a factorised band matrix (output of adsb_band_factorize / dgbtrf_) into `slot` of `axis`.
+ * Replaces ads::dim_data{M, ctx} (include/ads/solver.hpp:17-20). */
+int adsb_set_axis_factor(adsb_ctx* ctx, int axis, int slot, int n, int kl, int ku, int ldab,
+                         const double* ab, const int* ipiv);
+
+/* ---- managed coefficient tensors (cnt[0]*cnt[1]*cnt[2] doubles each, ids 0..ADSB_MAX_BUFFERS-1)
+ * Device mirrors of lin::tensor objects (include/ads/lin/tensor/tensor.hpp:14-50). */
+int adsb_upload(adsb_ctx* ctx, int buf, const double* host);
+int adsb_download(adsb_ctx* ctx, int buf, double* host);
+int adsb_swap(adsb_ctx* ctx, int buf_a, int buf_b);        /* std::swap(u, u_prev) */
+int adsb_zero(adsb_ctx* ctx, int buf);                      /* zero(rhs), tensor.hpp:44-50 */
+int adsb_bind(adsb_ctx* ctx, int buf, double* device_ptr);  /* adopt caller-owned device memory */
+double* adsb_device_ptr(adsb_ctx* ctx, int buf);
+
+/* Overwrite the hyper-plane index `idx` of `axis` with `values` (host, product of the other
+ * extents doubles).  Replaces the Dirichlet overwrite `v(0,i) = buf(i)` of
+ * examples/heat/heat_2d.hpp:40-47. */
+int adsb_set_plane(adsb_ctx* ctx, int buf, int axis, int idx, const double* values);
+
+/* ---- right-hand side:  rhs_a = sum_e sum_q [ alpha*u*v_a - sum_k beta[k]*d_k u*d_k v_a ] w J
+ *                                 + gamma * F_a
+ * the form of every compute_rhs() on the path (examples/heat/heat_3d.hpp:49-67,
+ * heat_2d.hpp:80-106, implicit/implicit.hpp:132-182, scalability/test3d.hpp:66-95).
+ * method ADSB_RHS_COLLAPSED applies the exactly pre-integrated 1-D quadrature operators
+ * (sum factorisation carried through the quadrature sums; HBM-bound);
+ * method ADSB_RHS_QUADRATURE evaluates u and grad u at every Gauss point and integrates against
+ * the test functions by sum factorisation (general pointwise forms; FP64-bound). */
+#define ADSB_RHS_COLLAPSED 0
+#define ADSB_RHS_QUADRATURE 1
+typedef struct {
+    double alpha;    /* coefficient of u*v */
+    double beta[3];  /* coefficient of d_k u * d_k v (pass +dt for "- dt * grad.grad") */
+    double gamma;    /* coefficient of the load tensor in `forcing_buf` (0: none) */
+    int forcing_buf; /* managed buffer id holding F, or -1 */
+    int method;      /* ADSB_RHS_COLLAPSED / ADSB_RHS_QUADRATURE */
+} adsb_form;
+int adsb_compute_rhs(adsb_ctx* ctx, const adsb_form* form, int src_buf, int dst_buf);
+
+/* Load tensor of a built-in source: F_a = sum_{e in supp(a)} sum_q f(x_q) [v_a(x_q)] w J.
+ * source 1: the scalability forcing (examples/scalability/test3d.hpp:58-64, test2d.hpp:49-54).
+ * with_test_function 0 reproduces the reference form, which adds dt*f(x_q)*w*J to every DOF of
+ * the element without the factor v_a (test3d.hpp:86-88). */
+int adsb_load_tensor(adsb_ctx* ctx, int source, int with_test_function, int dst_buf);
+
+/* L2-projection right-hand side of a built-in initial state (include/ads/projection.hpp:12-153):
+ * state 0 heat_3d bump (examples/heat/heat_3d.hpp:22-28), 1 implicit 2-D/3-D bump
+ * (examples/implicit/implicit.hpp:38-43), 2 constant one. */
+int adsb_project_init(adsb_ctx* ctx, int state, int dst_buf);
+
+/* ---- ADS solve: one batched banded forward/back substitution per axis, in place.
+ * Replaces ads::ads_solve(rhs, buffer, dims...) (include/ads/solver.hpp:35-41,:148-160,:222-226)
+ * i.e. 3 x { lin::solve_with_factorized -> dgbtrs_ (include/ads/lin/band_solve.hpp:21-31) +
+ * lin::cyclic_transpose (include/ads/lin/tensor/cyclic_transpose.hpp:54-63) }.  The tensor never
+ * moves: each sweep reads and writes the canonical layout.  slots[d] selects the factor of axis d. */
+int adsb_solve(adsb_ctx* ctx, int buf, const int* slots);
+
+/* One axis only (lin::solve_with_factorized on the axis-`axis` lines of the tensor). */
+int adsb_sweep(adsb_ctx* ctx, int buf, int axis, int slot);
+
+/* ---- whole steps resident on the device (simulation_base::run's loop body,
+ * src/ads/simulation/simulation_base.cpp:11-20 with step() of the examples):
+ *   repeat nsteps: for each sub-step s: swap(u, u_prev); rhs(form[s]) -> u; [planes]; solve(slots[s]) */
+typedef struct {
+    adsb_form form;
+    int slots[3];
+    int fix_axis;     /* -1, or axis whose plane 0 is overwritten before the solve (heat_2d) */
+    int fix_buf;      /* managed buffer holding the plane values in its first entries */
+} adsb_substep;
+int adsb_step(adsb_ctx* ctx, int u_buf, int uprev_buf, const adsb_substep* sub, int nsub, int nsteps);
+
+/* Device time (ms) spent in the stages since the last call: [0] rhs, [1..3] sweep per axis,
+ * [4] other.  Only collected when enabled (costs event records). */
+int adsb_enable_timing(adsb_ctx* ctx, int on);
+int adsb_stage_times(adsb_ctx* ctx, double* ms5);
+
+/* Number of kernels this context has launched so far. */
+long long adsb_launch_count(adsb_ctx* ctx);
+
+/* ============== pointer-level entry points (sharded runs; caller owns the memory) ===========
+ * A view is extents n[3] and element strides s[3] (doubles); unused axes have n = 1. */
+typedef struct {
+    int n[3];
+    long long s[3];
+} adsb_view;
+
+/* Sweep along `axis` over all lines of the view.  row_off_in/out (may be NULL) give, for each
+ * index j along the sweep axis, the element offset of that hyper-plane instead of j*s[axis]
+ * (host arrays of n[axis] entries): lets the sweep read / write the block layout of an all-to-all. */
+int adsb_sweep_view(adsb_ctx* ctx, int axis, int slot, const double* in, const adsb_view* vin,
+                    const long long* row_off_in, double* out, const adsb_view* vout,
+                    const long long* row_off_out);
+
+/* Collapsed RHS on a box: `in` covers [in_lo, in_lo+vin.n) in global DOF indices (with whatever
+ * halo the caller exchanged), `out` covers [out_lo, out_lo+vout.n).  Input outside the global
+ * domain is never read; input inside the domain but outside the `in` box is an error. */
+int adsb_rhs_view(adsb_ctx* ctx, const adsb_form* form, const double* in, const adsb_view* vin,
+                  const int* in_lo, const double* forcing, double* out, const adsb_view* vout,
+                  const int* out_lo);
+
+/* ---- introspection (used by the CPU test-suite to check the substitution plan without a GPU)
+ * Builds the chunked-substitution plan of a factor exactly as adsb_set_axis_factor does and copies
+ * it out.  dims[6] = {KL, KD, piv, CH, S, rows=S*CH}; arrays sized rows*KL (Lm, Phi), rows (pv,
+ * rinv), rows*KD (Ut, Psi), S*KL*KL (T); any output pointer may be NULL. */
+int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int* dims,
+                    double* Lm, int* pv, double* Ut, double* rinv, double* Phi, double* Psi, double* T);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ADSB200_H */

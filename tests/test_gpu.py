@@ -1,0 +1,218 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI,
+against (1) the reference's own known-answer tests, (2) golden vectors produced by the compiled
+unmodified reference (tests/golden/*.npz), (3) the CPU oracle on seeded inputs, and (4) at full
+size through size-independent properties.  Tolerances follow BASELINE.json: relative L2 <= 1e-12
+per step, <= 1e-10 after 100 steps."""
+import numpy as np
+import pytest
+
+import kats
+import iga_ads_b200 as ads
+from iga_ads_b200 import Form, U, U_PREV
+from oracle.oracle import NDIM, rel_l2, synthetic_state
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-12
+TOL_100 = 1e-10
+
+
+def make_ctx(shape, mats, kl, ku):
+    """Context with only factors (no quadrature tables): enough for ads_solve."""
+    ctx = ads.Context(shape)
+    for ax, m in enumerate(mats):
+        lu, piv = ads.band_factorize(m, kl[ax], ku[ax])
+        ctx.set_factor(ax, 0, lu, piv, kl[ax], ku[ax])
+    return ctx
+
+
+# ---------------------------------------------------------------------- K2: ads_solve
+@pytest.mark.parametrize("kat", [kats.ADS_2D, kats.ADS_3D], ids=["2d", "3d"])
+def test_ads_solve_reference_kats(kat):
+    # tests/ads/solver_test.cpp:101-255 (Mx needs pivoting); Catch Approx there, 1e-13 here
+    nd = len(kat["shape"])
+    ctx = make_ctx(kat["shape"], [kats.to_band(m, 1, 1) for m in kat["mats"]], [1] * nd, [1] * nd)
+    ctx.upload(U, np.array(kat["rhs"], dtype=float))
+    ctx.solve(U)
+    np.testing.assert_allclose(ctx.download(U), kat["expected"], rtol=1e-13, atol=1e-13)
+
+
+def test_ads_solve_1d_kat_and_band_solve_kat():
+    # tests/ads/solver_test.cpp:63-99 as a (4 x 1) tensor swept along axis 0
+    ctx = make_ctx((4, 1), [kats.to_band(kats.MX, 1, 1)], [1], [1])
+    ctx.upload(U, np.array(kats.ADS_1D["rhs"], dtype=float))
+    ctx.sweep(U, 0)
+    np.testing.assert_allclose(ctx.download(U), kats.ADS_1D["expected"], rtol=1e-13)
+    # tests/ads/lin/band_solve_test.cpp:16-46: kl=1, ku=2, n=6, 4 right-hand sides (abs 1e-5 there)
+    kl, ku, dense, b, x = kats.band_solve_kat()
+    ctx = make_ctx((6, 4), [kats.to_band(dense, kl, ku)], [kl], [ku])
+    ctx.upload(U, b)
+    ctx.sweep(U, 0)
+    got = ctx.download(U).reshape(b.shape)
+    assert np.abs(got - x).max() < 1e-5
+    np.testing.assert_allclose(got, np.linalg.solve(dense, b.T).T, rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["p2", "p3fix", "p5", "p4K"])
+def test_ads_solve_vs_golden(golden, tag):
+    g = golden["solve"]
+    p, ne, kind, fix = (int(v) for v in g[f"{tag}_meta"])
+    h = float(g[f"{tag}_h"][0])
+    m = ads.matrix_1d(kind, p, ne, h=h, fix=fix)
+    n = ne + p
+    for nd in (2, 3):
+        ctx = make_ctx((n,) * nd, [m] * nd, [p] * nd, [p] * nd)
+        ctx.upload(U, g[f"{tag}_{nd}d_rhs"])
+        ctx.solve(U)
+        assert rel_l2(ctx.download(U), g[f"{tag}_{nd}d_x"]) < 1e-13, (tag, nd)
+
+
+def test_ads_solve_mixed_shapes_vs_golden(golden):
+    g = golden["solve"]
+    mats = [ads.matrix_1d(0, p, ne) for p, ne in ((2, 12), (3, 7), (5, 6))]
+    ctx = make_ctx((14, 10, 11), mats, [2, 3, 5], [2, 3, 5])
+    ctx.upload(U, g["mixed_rhs"])
+    ctx.solve(U)
+    assert rel_l2(ctx.download(U), g["mixed_x"]) < 1e-13
+
+
+@pytest.mark.parametrize("p,ne,nd,kind,h,fix", [(2, 62, 3, 0, 0.0, 0), (5, 43, 3, 0, 0.0, 1), (3, 253, 2, 3, 0.005, 0),
+                                               (4, 60, 3, 3, 3.0, 1), (2, 510, 2, 0, 0.0, 0), (3, 29, 3, 0, 0.0, 0)])
+def test_ads_solve_vs_oracle_random(oracle, p, ne, nd, kind, h, fix):
+    """ragged sizes (n not a multiple of the chunk length / tile width), pivoting factors"""
+    n = ne + p
+    m = ads.matrix_1d(kind, p, ne, h=h, fix=fix)
+    lu, piv = ads.band_factorize(m, p, p)
+    rhs = np.random.default_rng(n).standard_normal(n ** nd)
+    want = oracle.ads_solve((n,) * nd, [lu] * nd, [piv] * nd, [p] * nd, [p] * nd, rhs)
+    ctx = make_ctx((n,) * nd, [m] * nd, [p] * nd, [p] * nd)
+    ctx.upload(U, rhs)
+    ctx.solve(U)
+    assert rel_l2(ctx.download(U), want) < 1e-13
+
+
+def test_single_axis_sweeps_match_oracle_dgbtrs(oracle):
+    """each axis alone == dgbtrs on the lines of that axis (rotation folded into the kernel)"""
+    p, shape = 2, (37, 21, 18)
+    nes = [s - p for s in shape]
+    mats = [ads.matrix_1d(0, p, ne) for ne in nes]
+    ctx = make_ctx(shape, mats, [p] * 3, [p] * 3)
+    rhs = np.random.default_rng(3).standard_normal(shape[::-1])  # [z][y][x] == x fastest
+    for ax in range(3):
+        lu, piv = ads.band_factorize(mats[ax], p, p)
+        lines = np.moveaxis(rhs, 2 - ax, -1)
+        want = oracle.solve_factorized(lu, piv, p, p, np.ascontiguousarray(lines)).reshape(lines.shape)
+        want = np.moveaxis(want, -1, 2 - ax)
+        ctx.upload(U, rhs)
+        ctx.sweep(U, ax)
+        assert rel_l2(ctx.download(U), want) < 1e-14, ax
+
+
+# ---------------------------------------------------------------------- K1 + whole steps vs golden
+def make_problem(name, p, ne, dt, nsteps=1):
+    sim = ads.PROBLEMS[name](p, ne, ads.timesteps_config(nsteps, dt))
+    sim.prepare_matrices()
+    return sim
+
+
+def _problem_tags(g):
+    return sorted(k[:-5] for k in g.files if k.endswith("_meta"))
+
+
+NAMES = {0: "heat_3d", 1: "heat_2d", 2: "implicit_2d", 3: "scalability_3d", 4: "scalability_2d", 5: "implicit_3d"}
+
+
+def test_rhs_and_steps_vs_reference_golden(golden):
+    """Every example on the path: each compute_rhs alone, one step and a short trajectory from the
+    synthetic state, against outputs of the compiled unmodified reference."""
+    g = golden["problems"]
+    tags = _problem_tags(g)
+    assert len(tags) >= 13
+    for tag in tags:
+        pid, p, ne, ns = (int(v) for v in g[tag + "_meta"])
+        dt = float(g[tag + "_dt"][0])
+        sim = make_problem(NAMES[pid], p, ne, dt)
+        u0 = g[tag + "_u0"]
+        subs = sim.substeps()
+        ctx = sim.ctx
+        for s, sub in enumerate(subs, start=1):
+            ctx.upload(U_PREV, u0)
+            ctx.compute_rhs(sub.form, U_PREV, U)
+            assert rel_l2(ctx.download(U), g[f"{tag}_rhs{s}"]) < 1e-13, (tag, s)
+        sim.set_state(u0)
+        sim.advance(1)
+        assert rel_l2(sim.state(), g[tag + "_syn_step1"]) < TOL_STEP, tag
+        steps = int(g[tag + "_syn_steps"][0])
+        sim.set_state(u0)
+        sim.advance(steps)
+        assert rel_l2(sim.state(), g[tag + "_syn"]) < steps * TOL_STEP, tag
+
+
+def test_heat3d_100_steps_vs_reference_golden(golden):
+    """BASELINE.json configs[0]: heat_3d p=2, 12^3, dt=1e-7, 100 steps from the shipped initial state."""
+    g = golden["problems"]
+    sim = make_problem("heat_3d", 2, 12, 1e-7)
+    sim.set_state(g["heat_3d_p2_n12_shipped_init"])
+    sim.advance(100)
+    u = sim.state()
+    assert rel_l2(u, g["heat_3d_p2_n12_shipped"]) < TOL_100
+    assert abs(u.sum() - 132.96044839648852) < 1e-8  # checksum recorded in BASELINE.md
+
+
+# ---------------------------------------------------------------------- vs the oracle, larger
+@pytest.mark.parametrize("name,p,ne,dt", [("heat_3d", 2, 62, 1e-7), ("heat_2d", 3, 253, 1e-5),
+                                          ("implicit_2d", 3, 200, 1e-2), ("implicit_3d", 3, 30, 1e-2),
+                                          ("scalability_3d", 2, 30, 1e-6), ("scalability_3d", 5, 20, 1e-6),
+                                          ("scalability_3d", 4, 21, 1e-6), ("scalability_2d", 3, 130, 1e-6)])
+def test_one_step_vs_oracle(oracle, name, p, ne, dt):
+    sim = make_problem(name, p, ne, dt)
+    u0 = synthetic_state(sim.shape())
+    sim.set_state(u0)
+    sim.advance(1)
+    want, _ = oracle.run(name, p, ne, dt, 1, u0=u0)
+    assert rel_l2(sim.state(), want) < TOL_STEP, name
+
+
+def test_heat2d_100_steps_vs_oracle(oracle):
+    sim = make_problem("heat_2d", 3, 48, 1e-5)
+    u0 = synthetic_state(sim.shape())
+    sim.set_state(u0)
+    sim.advance(100)
+    want, _ = oracle.run("heat_2d", 3, 48, 1e-5, 100, u0=u0)
+    assert rel_l2(sim.state(), want) < TOL_100
+
+
+# ---------------------------------------------------------------------- full size, by properties
+def test_full_size_512_properties():
+    """heat_3d p=2 on 512^3 (BASELINE.json configs[2], N = 135 796 744): the oracle cannot run this,
+    so check (a) M^-1 (M u) == u through rhs(alpha=1, beta=0) + solve, (b) linearity of a step."""
+    p, ne, dt = 2, 512, 1e-7
+    sim = make_problem("heat_3d", p, ne, dt)
+    ctx = sim.ctx
+    n = ne + p
+    rng = np.random.default_rng(1)
+    u0 = rng.standard_normal(n ** 3)
+    ctx.upload(U_PREV, u0)
+    ctx.compute_rhs(Form.make(1.0, (0.0, 0.0, 0.0)), U_PREV, U)  # rhs = (Mx (x) My (x) Mz) u
+    ctx.solve(U)
+    back = ctx.download(U)
+    assert rel_l2(back, u0) < 1e-11
+    # linearity: step(a*u + v) == a*step(u) + step(v)
+    v0 = rng.standard_normal(n ** 3)
+    outs = []
+    for w in (u0, v0, 0.5 * u0 + v0):
+        sim.set_state(w)
+        sim.advance(1)
+        outs.append(sim.state())
+    assert rel_l2(outs[2], 0.5 * outs[0] + outs[1]) < 1e-12
+
+
+def test_step_keeps_constants_for_pure_mass_form():
+    """rhs with beta = 0 followed by the solve is the identity on any state (2-D, p=3, ragged n)."""
+    sim = make_problem("implicit_2d", 3, 301, 1e-2)
+    ctx = sim.ctx
+    u0 = synthetic_state(sim.shape(), seed=9)
+    ctx.upload(U_PREV, u0)
+    ctx.compute_rhs(Form.make(1.0, (0.0, 0.0)), U_PREV, U)
+    ctx.solve(U)
+    assert rel_l2(ctx.download(U), u0) < 1e-12

@@ -1,0 +1,199 @@
+"""CPU tests of the product's host side (no GPU): the C-ABI library loads and exports what
+include/adsb200.h declares, the host setup reproduces the reference's tables / matrices / factors
+(golden vectors from the compiled reference), the chunked-substitution plan is algebraically the
+dgbtrs recurrence (emulated in numpy here and compared with the oracle), and the device entry
+points refuse to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import kats
+import iga_ads_b200 as ads
+from iga_ads_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "adsb200.h")).read()
+    declared = set(re.findall(r"\b(adsb_[a-z0-9_]+)\s*\(", header))
+    declared.discard("adsb_ctx")
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.load().adsb_abi_version() == 1
+
+
+def test_gauss_tables_knots_matrices_factors_vs_golden(golden):
+    g = golden["setup"]
+    for q in range(2, 8):
+        x, w = ads.gauss(q)
+        assert np.array_equal(x, g[f"gauss_x_{q}"]) and np.array_equal(w, g[f"gauss_w_{q}"])
+    for p, ne in ((1, 5), (2, 12), (3, 7), (4, 9), (5, 6)):
+        t = ads.basis_tables(p, ne)
+        for k in ("b", "x", "w", "J", "first_dof"):
+            assert np.array_equal(t[k], g[f"tab_{p}_{ne}_{k}"]), (p, ne, k)
+        assert np.array_equal(ads.knots(p, ne), g[f"tab_{p}_{ne}_knots"])
+        for kind, h, fix in ((0, 0.0, 0), (0, 0.0, 1), (1, 0.0, 0), (2, 0.0, 0), (3, 0.005, 0), (3, 3.0, 1)):
+            tag = f"mat_{p}_{ne}_{kind}_{fix}_{h}"
+            m = ads.matrix_1d(kind, p, ne, h=h, fix=fix)
+            assert np.array_equal(m, g[tag]), tag
+            if kind in (0, 3):
+                lu, piv = ads.band_factorize(m, p, p)
+                assert np.array_equal(piv, g[tag + "_ipiv"]), tag
+                np.testing.assert_allclose(lu, g[tag + "_lu"], rtol=1e-14, atol=1e-300)
+
+
+def test_bspline_kats():
+    # tests/ads/bspline/bspline_test.cpp:14-68, eval_test.cpp:24-78
+    k = ads.knots(2, 4)
+    assert np.array_equal(k, [0, 0, 0, 0.25, 0.5, 0.75, 1, 1, 1])
+    for x, s in ((-1, 2), (2.0, 5), (0.0, 2), (1.0, 5), (0.25, 3), (0.75, 5), (0.1, 2), (0.9, 5)):
+        assert ads.find_span(x, k, 2) == s
+    k = ads.knots(2, 5)
+    for i in range(101):
+        x = i / 100
+        d = ads.basis_ders(ads.find_span(x, k, 2), x, k, 2, 2)
+        assert abs(d[0].sum() - 1) < 1e-12 and abs(d[1].sum()) < 1e-7 and abs(d[2].sum()) < 1e-7
+
+
+def test_dimension_mirror_fix_and_factor(golden):
+    g = golden["setup"]
+    d = ads.dimension(ads.dim_config(3, 7))
+    assert d.dofs() == 10
+    d.fix_left()
+    assert np.array_equal(d.M, g["mat_3_7_0_1_0.0"])
+    lu, piv = d.factorize_matrix()
+    assert np.array_equal(piv, g["mat_3_7_0_1_0.0_ipiv"])
+
+
+def test_factorize_reference_kat_pivots_and_singular():
+    lu, piv = ads.band_factorize(kats.to_band(kats.MX, 1, 1), 1, 1)
+    assert piv[0] == 2  # tests/ads/solver_test.cpp: Mx needs a row interchange
+    with pytest.raises(ads.AdsbError) as e:
+        ads.band_factorize(kats.to_band(np.zeros((3, 3)), 1, 1), 1, 1)
+    assert e.value.code == -3
+
+
+# ------------------------------------------------------------------ the substitution plan
+def get_plan(lu, ipiv, kl, ku):
+    lib = _lib.load()
+    lu = np.ascontiguousarray(lu)
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    n, ldab = lu.shape
+    dims = np.zeros(6, dtype=np.int32)
+    none = None
+    _lib.check(lib.adsb_sweep_plan(n, kl, ku, ldab, _lib.d_(lu), _lib.i_(ipiv), _lib.i_(dims), none, none,
+                                   none, none, none, none, none))
+    KL, KD, piv, CH, S, rows = (int(v) for v in dims)
+    P = dict(KL=KL, KD=KD, piv=piv, CH=CH, S=S, n=n, Lm=np.zeros((rows, KL)), pv=np.zeros(rows, dtype=np.int32),
+             Ut=np.zeros((rows, KD)), rinv=np.zeros(rows), Phi=np.zeros((rows, KL)), Psi=np.zeros((rows, KD)),
+             T=np.zeros((S, KL, KL)))
+    _lib.check(lib.adsb_sweep_plan(n, kl, ku, ldab, _lib.d_(lu), _lib.i_(ipiv), _lib.i_(dims), _lib.d_(P["Lm"]),
+                                   _lib.i_(P["pv"]), _lib.d_(P["Ut"]), _lib.d_(P["rinv"]), _lib.d_(P["Phi"]),
+                                   _lib.d_(P["Psi"]), _lib.d_(P["T"])))
+    return P
+
+
+def emulate_chunked_sweep(P, b):
+    """numpy transcription of sweep_kernel's five phases for one line (tests only)."""
+    KL, KD, CH, S, n = P["KL"], P["KD"], P["CH"], P["S"], P["n"]
+    bp = np.zeros(S * CH + KL)
+    bp[:n] = b
+    v = np.zeros((S, CH + KL))
+    fst = np.zeros((S, KL))
+    for s in range(S):                                  # F1
+        j0 = s * CH
+        v[s] = bp[j0:j0 + CH + KL]
+        o = v[s, CH:].copy()
+        for i in range(CH):
+            t = P["pv"][j0 + i]
+            if t:
+                v[s, i], v[s, i + t] = v[s, i + t], v[s, i]
+            for r in range(1, KL + 1):
+                v[s, i + r] -= P["Lm"][j0 + i, r - 1] * v[s, i]
+        fst[s] = v[s, CH:] - o
+    d = np.zeros(KL)                                    # F2
+    delta = np.zeros((S, KL))
+    for s in range(S - 1):
+        d = fst[s] + P["T"][s] @ d
+        delta[s + 1] = d
+    bst = np.zeros((S, KD))
+    for s in range(S):                                  # B1
+        j0 = s * CH
+        for i in range(CH - 1, -1, -1):
+            acc = v[s, i] + P["Phi"][j0 + i] @ delta[s]
+            for k in range(KD, 0, -1):
+                if i + k < CH:
+                    acc -= P["Ut"][j0 + i, k - 1] * v[s, i + k]
+            v[s, i] = acc * P["rinv"][j0 + i]
+        bst[s] = v[s, :KD]
+    t = np.zeros(KD)                                    # B2
+    tin = np.zeros((S, KD))
+    for s in range(S - 1, 0, -1):
+        t = bst[s] + P["Psi"][s * CH:s * CH + KD] @ t
+        tin[s - 1] = t
+    x = np.zeros(S * CH)
+    for s in range(S):                                  # B3
+        j0 = s * CH
+        x[j0:j0 + CH] = v[s, :CH] + P["Psi"][j0:j0 + CH] @ tin[s]
+    return x[:n]
+
+
+PLAN_CASES = [
+    # (p, elements, kind, h, fix)
+    (1, 40, 0, 0.0, 0), (2, 12, 0, 0.0, 0), (2, 100, 0, 0.0, 1), (3, 70, 0, 0.0, 0), (3, 64, 3, 0.005, 0),
+    (4, 66, 0, 0.0, 0), (5, 64, 0, 0.0, 0), (5, 61, 0, 0.0, 1), (4, 70, 3, 3.0, 1), (2, 33, 3, 3.0, 3),
+    (5, 28, 3, 0.5, 0), (2, 31, 0, 0.0, 0), (2, 64, 0, 0.0, 0),
+]
+
+
+@pytest.mark.parametrize("p,ne,kind,h,fix", PLAN_CASES)
+def test_chunked_plan_is_dgbtrs(oracle, p, ne, kind, h, fix):
+    ab = ads.matrix_1d(kind, p, ne, h=h, fix=fix)
+    lu, piv = ads.band_factorize(ab, p, p)
+    P = get_plan(lu, piv, p, p)
+    assert P["KL"] >= p and P["S"] == -(-(ne + p) // P["CH"])
+    rng = np.random.default_rng(p * 100 + ne)
+    b = rng.standard_normal(ne + p)
+    want = oracle.solve_factorized(lu, piv, p, p, b)
+    got = emulate_chunked_sweep(P, b)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13, (P["piv"], P["KL"], P["KD"])
+
+
+def test_plan_covers_pivoting_and_plain_variants():
+    lu, piv = ads.band_factorize(ads.matrix_1d(0, 2, 64), 2, 2)
+    P = get_plan(lu, piv, 2, 2)
+    assert (P["piv"], P["KL"], P["KD"]) == (0, 2, 2)      # Gram p=2: no interchange, U keeps ku
+    lu, piv = ads.band_factorize(ads.matrix_1d(0, 5, 64), 5, 5)
+    P = get_plan(lu, piv, 5, 5)
+    assert (P["piv"], P["KL"], P["KD"]) == (1, 5, 10)     # Gram p=5 pivots
+
+
+def test_plan_general_band_kat(oracle):
+    # tests/ads/lin/band_solve_test.cpp:16-46 -- kl=1, ku=2, n=6, 4 right-hand sides
+    kl, ku, dense, b, x = kats.band_solve_kat()
+    lu, piv = ads.band_factorize(kats.to_band(dense, kl, ku), kl, ku)
+    P = get_plan(lu, piv, kl, ku)
+    for r in range(b.shape[0]):
+        got = emulate_chunked_sweep(P, b[r])
+        assert np.abs(got - x[r]).max() < 1e-5
+        np.testing.assert_allclose(got, np.linalg.solve(dense, b[r]), rtol=1e-12)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ads.AdsbError) as e:
+        ads.Context((14, 14, 14))
+    assert e.value.code == -2
+    with pytest.raises(ads.AdsbError):
+        sim = ads.heat_3d(2, 4, ads.timesteps_config(1, 1e-7))
+        sim.prepare_matrices()
