@@ -96,7 +96,7 @@ _SIGNATURES = {
     "adsb_stage_times": (c_int, [vp, dp]),
     "adsb_launch_count": (c_ll, [vp]),
     "adsb_sweep_view": (c_int, [vp, c_int, c_int, vp, ctypes.POINTER(View), llp, vp, ctypes.POINTER(View), llp]),
-    "adsb_sweep_plan": (c_int, [c_int, c_int, c_int, c_int, dp, ip, ip, dp, ip, dp, dp, dp, dp, dp]),
+    "adsb_sweep_plan": (c_int, [c_int, c_int, c_int, c_int, dp, ip, ip, ip, dp, dp, dp, dp, dp, dp, dp]),
     "adsb_rhs_view": (c_int, [vp, ctypes.POINTER(Form), vp, ctypes.POINTER(View), ip, vp, vp,
                               ctypes.POINTER(View), ip]),
 }

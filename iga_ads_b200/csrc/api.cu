@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <string>
@@ -27,6 +28,8 @@ struct AxisData {
     std::vector<double> bt, xq, w, J;  // host copies (layout of adsb_basis_tables)
     double* d_M = nullptr;             // [n][2p+1] Gram rows
     double* d_S = nullptr;             // [n][2p+1] stiffness rows
+    double* d_MT = nullptr;            // [n][2p+1] Gram columns: row k holds A(k-p..k+p, k)
+    double* d_ST = nullptr;
     double* d_bt = nullptr;            // device copy of bt
     double* d_xq = nullptr;
     double* d_wJ = nullptr;            // [elements][q] w[k]*J[e]
@@ -131,9 +134,9 @@ struct StageTimer {
     }
 };
 
-int pick_nl(int S) {
-    int nl = 64;
-    while (nl > 4 && nl * S > 384) nl >>= 1;
+int pick_nl(int SC) {  // lanes per CTA (each thread carries SWEEP_RL lines)
+    int nl = 32;
+    while (nl > 2 && nl * SC > 512) nl >>= 1;
     return nl;
 }
 
@@ -191,14 +194,19 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     G.s0_out = vo.s[l0];
     G.s1_in = vi.s[l1];
     G.s1_out = vo.s[l1];
-    G.pitch = F.n | 1;
-    int NL = pick_nl(F.S);
+    G.pitch = F.n + (F.n & 1);
+    if (G.pitch % 4 == 0) G.pitch += 2;  // pitch = 2 (mod 4): conflict-free 128-bit column access
+    G.bulk = 0;
+    int NL = pick_nl(F.SC);
     if (contig) {
-        while (NL > 1 && sweep_smem_bytes(F, true, NL, G.pitch) > 100 * 1024) NL >>= 1;
+        while (NL > 1 && sweep_smem_bytes(F, true, NL, G.pitch) > 200 * 1024) NL >>= 1;
         if (sweep_smem_bytes(F, true, NL, G.pitch) > 220 * 1024)
             return fail(ADSB_EINVAL, "sweep: line too long for the shared-memory staged x sweep");
+        const bool aligned = ((uintptr_t) in % 16 == 0) && ((uintptr_t) out % 16 == 0) && F.n % 2 == 0 &&
+                             G.s0_in % 2 == 0 && G.s1_in % 2 == 0 && G.s0_out % 2 == 0 && G.s1_out % 2 == 0;
+        G.bulk = aligned ? 1 : 0;
     }
-    if (NL * F.S > 512) return fail(ADSB_EINVAL, "sweep: axis too long for the compiled chunking (n <= 4224)");
+    if (NL * F.SC > 512) return fail(ADSB_EINVAL, "sweep: axis too long for the compiled chunking");
     if (G.L1 > 65535) return fail(ADSB_EINVAL, "sweep: outer extent beyond grid limits");
     StageTimer t(c, 1 + axis);
     cudaError_t e = (cudaError_t) launch_sweep(F, G, contig, NL, c->stream);
@@ -227,8 +235,8 @@ int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view&
     ops.Sx = c->ax[0].d_S;
     ops.My = c->ax[1].d_M;
     ops.Sy = c->ax[1].d_S;
-    ops.Mz = c->ndim == 3 ? c->ax[2].d_M : nullptr;
-    ops.Sz = c->ndim == 3 ? c->ax[2].d_S : nullptr;
+    ops.MzT = c->ndim == 3 ? c->ax[2].d_MT : nullptr;
+    ops.SzT = c->ndim == 3 ? c->ax[2].d_ST : nullptr;
     RhsGeom g{};
     g.in = in;
     g.out = out;
@@ -271,6 +279,18 @@ int rows_from_band(int n, int p, const std::vector<double>& ab, std::vector<doub
     return ADSB_OK;
 }
 
+// column table: out[k][d] = A(k - p + d, k)
+int cols_from_band(int n, int p, const std::vector<double>& ab, std::vector<double>& cols) {
+    const int W = 2 * p + 1, ldab = 3 * p + 1;
+    cols.assign((size_t) n * W, 0.0);
+    for (int k = 0; k < n; ++k)
+        for (int d = 0; d < W; ++d) {
+            const int i = k - p + d;
+            if (i >= 0 && i < n) cols[(size_t) k * W + d] = ab[(size_t) k * ldab + 2 * p + i - k];
+        }
+    return ADSB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -309,6 +329,8 @@ int adsb_destroy(adsb_ctx* c) {
     for (auto& a : c->ax) {
         cudaFree(a.d_M);
         cudaFree(a.d_S);
+        cudaFree(a.d_MT);
+        cudaFree(a.d_ST);
         cudaFree(a.d_bt);
         cudaFree(a.d_xq);
         cudaFree(a.d_wJ);
@@ -363,6 +385,9 @@ int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int 
     std::vector<double> ab((size_t) (3 * p + 1) * a.n), rows;
     cudaFree(a.d_M);
     cudaFree(a.d_S);
+    cudaFree(a.d_MT);
+    cudaFree(a.d_ST);
+    a.d_MT = a.d_ST = nullptr;
     cudaFree(a.d_bt);
     cudaFree(a.d_xq);
     cudaFree(a.d_wJ);
@@ -372,9 +397,13 @@ int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int 
     if (int rc = matrix_from_tables(0, 0.0, p, elements, q, ders, b_flat, w, J, ab.data())) return rc;
     rows_from_band(a.n, p, ab, rows);
     if (int rc = upload_vec(rows, 0, &a.d_M, nullptr)) return rc;
+    cols_from_band(a.n, p, ab, rows);
+    if (int rc = upload_vec(rows, 0, &a.d_MT, nullptr)) return rc;
     if (int rc = matrix_from_tables(1, 0.0, p, elements, q, ders, b_flat, w, J, ab.data())) return rc;
     rows_from_band(a.n, p, ab, rows);
     if (int rc = upload_vec(rows, 0, &a.d_S, nullptr)) return rc;
+    cols_from_band(a.n, p, ab, rows);
+    if (int rc = upload_vec(rows, 0, &a.d_ST, nullptr)) return rc;
     if (int rc = upload_vec(a.bt, 0, &a.d_bt, nullptr)) return rc;
     if (int rc = upload_vec(a.xq, 0, &a.d_xq, nullptr)) return rc;
     std::vector<double> wJ((size_t) elements * q);
@@ -394,22 +423,23 @@ int adsb_set_axis_factor(adsb_ctx* c, int axis, int slot, int n, int kl, int ku,
     if (n != c->ng[axis]) return fail(ADSB_EINVAL, "set_axis_factor: n != n_global[axis]");
     if (kl < 0 || ku < 0 || ldab < 2 * kl + ku + 1) return fail(ADSB_EINVAL, "set_axis_factor: bad band shape");
     if (int rc = select_device(c)) return rc;
+    static_assert(SWEEP_MAX_DEPTH == SWEEP_MAX_DEPTH_DEV, "depth constants out of sync");
     SweepPlan P;
-    if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, P)) return rc;
+    if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, 1, P)) return rc;
     DevFactor& D = c->ax[axis].fac[slot];
     CU(cudaStreamSynchronize(c->stream));
     free_factor(D);
-    const size_t rows = (size_t) P.S * P.CH;
-    double *Lm, *Ut, *rinv, *Phi, *Psi, *T;
+    double *cfF, *cfB, *cfC, *T, *Rm, *W, *V;
     int* pv;
-    if (int rc = upload_vec(P.Lm, rows * P.KL, &Lm, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.pv, rows, &pv, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.Ut, rows * P.KD, &Ut, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.rinv, rows, &rinv, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.Phi, rows * P.KL, &Phi, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.Psi, rows * P.KD, &Psi, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.cfF, 0, &cfF, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.cfB, 0, &cfB, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.cfC, 0, &cfC, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.pv, 0, &pv, &D.allocs)) return rc;
     if (int rc = upload_vec(P.T, 0, &T, &D.allocs)) return rc;
-    D.f = SweepFactor{Lm, pv, Ut, rinv, Phi, Psi, T, P.n, P.S, P.KL, P.KD, P.piv};
+    if (int rc = upload_vec(P.Rm, 0, &Rm, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.W, 0, &W, &D.allocs)) return rc;
+    if (int rc = upload_vec(P.V, 0, &V, &D.allocs)) return rc;
+    D.f = SweepFactor{cfF, cfB, cfC, pv, T, Rm, W, V, P.n, P.ST, P.SC, P.KL, P.KD, P.piv, P.DF, P.DB, P.seq};
     D.set = true;
     return ADSB_OK;
 }
@@ -642,26 +672,26 @@ int adsb_project_init(adsb_ctx* c, int state, int dst) {
     return ADSB_OK;
 }
 
-int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int* dims, double* Lm,
-                    int* pv, double* Ut, double* rinv, double* Phi, double* Psi, double* T) {
+int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int* dims, int* pv,
+                    double* cfF, double* cfB, double* cfC, double* T, double* Rm, double* W, double* V) {
     SweepPlan P;
-    if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, P)) return rc;
-    const size_t rows = (size_t) P.S * P.CH;
+    if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, 1, P)) return rc;
     if (dims) {
-        dims[0] = P.KL; dims[1] = P.KD; dims[2] = P.piv; dims[3] = P.CH; dims[4] = P.S; dims[5] = (int) rows;
+        const int d[16] = {P.KL, P.KD, P.piv, P.CH, P.R, P.SC, P.ST, P.rows, P.LF, P.LB, P.LC, P.DF, P.DB, P.seq,
+                           SWEEP_MAX_DEPTH, 0};
+        std::copy(d, d + 16, dims);
     }
-    auto put = [](auto* dst, const auto& v, size_t padded) {
-        if (!dst) return;
-        std::fill(dst, dst + padded, 0);
-        std::copy(v.begin(), v.end(), dst);
+    auto put = [](auto* dst, const auto& v) {
+        if (dst) std::copy(v.begin(), v.end(), dst);
     };
-    put(Lm, P.Lm, rows * P.KL);
-    put(pv, P.pv, rows);
-    put(Ut, P.Ut, rows * P.KD);
-    put(rinv, P.rinv, rows);
-    put(Phi, P.Phi, rows * P.KL);
-    put(Psi, P.Psi, rows * P.KD);
-    put(T, P.T, P.T.size());
+    put(pv, P.pv);
+    put(cfF, P.cfF);
+    put(cfB, P.cfB);
+    put(cfC, P.cfC);
+    put(T, P.T);
+    put(Rm, P.Rm);
+    put(W, P.W);
+    put(V, P.V);
     return ADSB_OK;
 }
 

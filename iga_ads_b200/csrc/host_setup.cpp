@@ -268,12 +268,35 @@ int band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv) {
 
 // ---------------------------------------------------------------------------------------------
 // Plan for the chunk-parallel substitution kernel (kernels_sweep.cu).  A line of n unknowns is cut
-// into S chunks of CH columns.  Each chunk runs the forward / backward recurrences from a zero
-// incoming state; the exact result is recovered as local + (homogeneous response) * (true
-// incoming state), where the states are chained by a short scan over chunks.  All homogeneous
-// responses depend only on the factor, so they are tabulated here once.
+// into SC chunks of CH columns.  Each chunk runs the pivoted forward recurrence and then the back
+// substitution from ZERO incoming states (local pass); the exact dgbtrs result is recovered as
+//     x = x_local + Xi * delta_c + Psi * t_c
+// delta_c : true forward state entering chunk c (KL partially updated rows),
+// t_c     : true first KD unknowns right of chunk c,
+// chained across chunks by  delta_{c+1} = Delta_c + T_c delta_c   and   t_{c-1} = X_c + R_c t_c,
+// X_c = xfirst_local_c + Xi_first_c delta_c.  All response tables depend only on the factor, so
+// they are tabulated here once.  Because the responses decay, the chains are evaluated to a finite
+// depth D in parallel (delta_c = sum_{d<=D} W_{c,d} Delta_{c-d}); the depth is chosen so that the
+// dropped products are below 1e-22 -- if that needs more than MAX_DEPTH terms the kernel falls
+// back to the sequential chain (seq = 1).
 // ---------------------------------------------------------------------------------------------
-int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch,
+namespace {
+void matmul(int K, const double* A, const double* B, double* C) {  // C = A*B, K x K row-major
+    for (int r = 0; r < K; ++r)
+        for (int c = 0; c < K; ++c) {
+            double acc = 0;
+            for (int m = 0; m < K; ++m) acc += A[r * K + m] * B[m * K + c];
+            C[r * K + c] = acc;
+        }
+}
+double maxabs(const double* A, int count) {
+    double m = 0;
+    for (int i = 0; i < count; ++i) m = std::max(m, std::fabs(A[i]));
+    return m;
+}
+}  // namespace
+
+int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch, int group,
                      SweepPlan& P) {
     const int kd = kl + ku;
     bool piv = false;
@@ -293,58 +316,115 @@ int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const in
     int var = piv ? std::max({kl, (kd_eff + 1) / 2, 1}) : std::max({kl, kd_eff, 1});
     if (var > 5) return fail(ADSB_EINVAL, "factor: bandwidth beyond the compiled kernel variants (p <= 5)");
     const int KL = var, KD = piv ? 2 * var : var;
-    P.n = n; P.KL = KL; P.KD = KD; P.piv = piv ? 1 : 0; P.CH = ch;
-    const int S = (n + ch - 1) / ch;
-    P.S = S;
-    P.Lm.assign(static_cast<size_t>(n) * KL, 0.0);
-    P.pv.assign(n, 0);
-    P.Ut.assign(static_cast<size_t>(n) * KD, 0.0);
-    P.rinv.assign(n, 0.0);
-    P.Phi.assign(static_cast<size_t>(n) * KL, 0.0);
-    P.Psi.assign(static_cast<size_t>(n) * KD, 0.0);
-    P.T.assign(static_cast<size_t>(S) * KL * KL, 0.0);
+    if (ch < KD) return fail(ADSB_EINVAL, "factor: chunk shorter than the band");
+    const int ST = ((n + ch - 1) / ch + group - 1) / group;  // threads per line
+    const int SC = ST * group;                                // chunks per line (some may be empty)
+    const size_t rows = static_cast<size_t>(SC) * ch + KL + KD;
+    P.n = n; P.KL = KL; P.KD = KD; P.piv = piv ? 1 : 0; P.CH = ch; P.R = group; P.SC = SC; P.ST = ST;
+    P.LF = KL + (KL & 1); P.LB = (KD + 1) + ((KD + 1) & 1); P.LC = (KD + KL) + ((KD + KL) & 1);
+    P.rows = static_cast<int>(rows);
+    std::vector<double> Lm(rows * KL, 0.0), Ut(rows * KD, 0.0), rinv(rows, 0.0), Phi(rows * KL, 0.0),
+        Psi(rows * KD, 0.0), Xi(rows * KL, 0.0), T(static_cast<size_t>(SC) * KL * KL, 0.0),
+        Rm(static_cast<size_t>(SC) * KD * KD, 0.0);
+    P.pv.assign(rows, 0);
     for (int j = 0; j < n; ++j) {
         const int lm = std::min(kl, n - 1 - j);
-        for (int i = 0; i < lm; ++i) P.Lm[static_cast<size_t>(j) * KL + i] = Aat(kd + 1 + i, j);
+        for (int i = 0; i < lm; ++i) Lm[static_cast<size_t>(j) * KL + i] = Aat(kd + 1 + i, j);
         P.pv[j] = ipiv[j] - 1 - j;
-        for (int k = 1; k <= kd_eff && j + k < n; ++k) P.Ut[static_cast<size_t>(j) * KD + k - 1] = Aat(kd - k, j + k);
-        P.rinv[j] = 1.0 / Aat(kd, j);
+        for (int k = 1; k <= kd_eff && j + k < n; ++k) Ut[static_cast<size_t>(j) * KD + k - 1] = Aat(kd - k, j + k);
+        rinv[j] = 1.0 / Aat(kd, j);
     }
-    // forward responses: unit perturbation of window row r at the chunk start, zero data after it
-    std::vector<double> win(ch + KL);
-    for (int s = 0; s < S; ++s) {
-        const int j0 = s * ch;
+    std::vector<double> win(ch + KL), xs(ch + KD);
+    for (int c = 0; c < SC; ++c) {
+        const int j0 = c * ch;
+        // forward response to a unit perturbation of window row r at the chunk start
         for (int r = 0; r < KL; ++r) {
             std::fill(win.begin(), win.end(), 0.0);
             win[r] = 1.0;
-            for (int i = 0; i < ch && j0 + i < n; ++i) {
-                const int j = j0 + i;
+            for (int i = 0; i < ch; ++i) {
+                const size_t j = static_cast<size_t>(j0) + i;
                 const int t = P.pv[j];
                 if (t) std::swap(win[i], win[i + t]);
-                for (int m = 1; m <= KL; ++m) win[i + m] = std::fma(-P.Lm[static_cast<size_t>(j) * KL + m - 1], win[i], win[i + m]);
-                P.Phi[static_cast<size_t>(j) * KL + r] = win[i];
+                for (int m = 1; m <= KL; ++m) win[i + m] = std::fma(-Lm[j * KL + m - 1], win[i], win[i + m]);
+                Phi[j * KL + r] = win[i];
             }
-            if (j0 + ch <= n)
-                for (int m = 0; m < KL; ++m) P.T[(static_cast<size_t>(s) * KL + m) * KL + r] = win[ch + m];
+            for (int m = 0; m < KL; ++m) T[(static_cast<size_t>(c) * KL + m) * KL + r] = win[ch + m];
+            // its image under the local back substitution (zero state on the right)
+            std::fill(xs.begin(), xs.end(), 0.0);
+            for (int i = ch - 1; i >= 0; --i) {
+                const size_t j = static_cast<size_t>(j0) + i;
+                double acc = Phi[j * KL + r];
+                for (int m = KD; m >= 1; --m) acc = std::fma(-Ut[j * KD + m - 1], xs[i + m], acc);
+                xs[i] = acc * rinv[j];
+                Xi[j * KL + r] = xs[i];
+            }
         }
-    }
-    // backward responses: unit value of the k-th unknown right of the chunk, zero data
-    std::vector<double> xs(ch + KD);
-    for (int s = 0; s < S; ++s) {
-        const int j0 = s * ch;
+        // backward response to a unit value of the k-th unknown right of the chunk
         for (int k = 0; k < KD; ++k) {
             std::fill(xs.begin(), xs.end(), 0.0);
             xs[ch + k] = 1.0;
             for (int i = ch - 1; i >= 0; --i) {
-                const int j = j0 + i;
-                if (j >= n) continue;
+                const size_t j = static_cast<size_t>(j0) + i;
                 double acc = 0;
-                for (int m = KD; m >= 1; --m) acc = std::fma(-P.Ut[static_cast<size_t>(j) * KD + m - 1], xs[i + m], acc);
-                xs[i] = acc * P.rinv[j];
-                P.Psi[static_cast<size_t>(j) * KD + k] = xs[i];
+                for (int m = KD; m >= 1; --m) acc = std::fma(-Ut[j * KD + m - 1], xs[i + m], acc);
+                xs[i] = acc * rinv[j];
+                Psi[j * KD + k] = xs[i];
+            }
+            for (int i = 0; i < KD; ++i) Rm[(static_cast<size_t>(c) * KD + i) * KD + k] = xs[i];
+        }
+    }
+    // chained products and the depth at which they vanish
+    const int MD = SWEEP_MAX_DEPTH;
+    P.W.assign(static_cast<size_t>(SC) * (MD - 1) * KL * KL, 0.0);
+    P.V.assign(static_cast<size_t>(SC) * (MD - 1) * KD * KD, 0.0);
+    int DF = 1, DB = 1;
+    // growing responses (stiffness-dominated K = M + hS far from diagonal dominance): explicit
+    // products of the transfer matrices would cancel catastrophically -> chain sequentially
+    bool seq = maxabs(T.data(), static_cast<int>(T.size())) > 1.0 || maxabs(Rm.data(), static_cast<int>(Rm.size())) > 1.0;
+    std::vector<double> cur(std::max(KL * KL, KD * KD)), nxt(cur.size());
+    const double tiny = 1e-22;
+    for (int c = 0; c < SC; ++c) {
+        // forward: delta_c = Delta_{c-1} + T_{c-1} Delta_{c-2} + T_{c-1} T_{c-2} Delta_{c-3} + ...
+        if (c >= 2) {
+            std::copy(&T[static_cast<size_t>(c - 1) * KL * KL], &T[static_cast<size_t>(c - 1) * KL * KL] + KL * KL, cur.begin());
+            for (int d = 2; c - d >= 0; ++d) {
+                if (maxabs(cur.data(), KL * KL) < tiny) break;
+                if (d > MD) { seq = true; break; }
+                std::copy(cur.begin(), cur.begin() + KL * KL, &P.W[(static_cast<size_t>(c) * (MD - 1) + d - 2) * KL * KL]);
+                DF = std::max(DF, d);
+                if (c - d - 1 < 0) break;
+                matmul(KL, cur.data(), &T[static_cast<size_t>(c - d) * KL * KL], nxt.data());
+                std::swap(cur, nxt);
+            }
+        }
+        // backward: t_c = X_{c+1} + R_{c+1} X_{c+2} + R_{c+1} R_{c+2} X_{c+3} + ...
+        if (c + 2 < SC) {
+            std::copy(&Rm[static_cast<size_t>(c + 1) * KD * KD], &Rm[static_cast<size_t>(c + 1) * KD * KD] + KD * KD, cur.begin());
+            for (int d = 2; c + d < SC; ++d) {
+                if (maxabs(cur.data(), KD * KD) < tiny) break;
+                if (d > MD) { seq = true; break; }
+                std::copy(cur.begin(), cur.begin() + KD * KD, &P.V[(static_cast<size_t>(c) * (MD - 1) + d - 2) * KD * KD]);
+                DB = std::max(DB, d);
+                if (c + d + 1 >= SC) break;
+                matmul(KD, cur.data(), &Rm[static_cast<size_t>(c + d) * KD * KD], nxt.data());
+                std::swap(cur, nxt);
             }
         }
     }
+    P.DF = DF; P.DB = DB; P.seq = seq ? 1 : 0;
+    // packed per-column records
+    P.cfF.assign(rows * P.LF, 0.0);
+    P.cfB.assign(rows * P.LB, 0.0);
+    P.cfC.assign(rows * P.LC, 0.0);
+    for (size_t j = 0; j < rows; ++j) {
+        for (int m = 0; m < KL; ++m) P.cfF[j * P.LF + m] = Lm[j * KL + m];
+        for (int k = 0; k < KD; ++k) P.cfB[j * P.LB + k] = Ut[j * KD + k];
+        P.cfB[j * P.LB + KD] = rinv[j];
+        for (int k = 0; k < KD; ++k) P.cfC[j * P.LC + k] = Psi[j * KD + k];
+        for (int m = 0; m < KL; ++m) P.cfC[j * P.LC + KD + m] = Xi[j * KL + m];
+    }
+    P.T = std::move(T);
+    P.Rm = std::move(Rm);
     return ADSB_OK;
 }
 

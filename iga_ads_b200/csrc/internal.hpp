@@ -20,18 +20,23 @@ int matrix_from_tables(int kind, double h, int p, int elements, int q, int ders,
 int matrix_1d(int kind, int p, int elements, double a, double b, double h, int fix, double* ab);
 int band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv);
 
+constexpr int SWEEP_MAX_DEPTH = 6;  // longest parallel state chain; beyond it the kernel chains sequentially
+
 // Host image of one factor prepared for the chunk-parallel sweep kernel (see host_setup.cpp).
 struct SweepPlan {
-    int n = 0, KL = 0, KD = 0, piv = 0, CH = 0, S = 0;
-    std::vector<double> Lm;    // [n][KL]   multipliers of column j (rows j+1..j+KL), zero padded
-    std::vector<int> pv;       // [n]       pivot row offset of column j (0..KL)
-    std::vector<double> Ut;    // [n][KD]   U(j, j+1..j+KD), zero padded
-    std::vector<double> rinv;  // [n]       1 / U(j,j)
-    std::vector<double> Phi;   // [n][KL]   forward response of row j to the chunk's incoming state
-    std::vector<double> Psi;   // [n][KD]   backward response of row j to the chunk's incoming state
-    std::vector<double> T;     // [S][KL][KL] forward state transfer across a whole chunk
+    int n = 0, KL = 0, KD = 0, piv = 0, CH = 0, R = 0, SC = 0, ST = 0, rows = 0;
+    int LF = 0, LB = 0, LC = 0;  // doubles per column in cfF / cfB / cfC (even, 16 B aligned records)
+    int DF = 1, DB = 1, seq = 0; // chain depths (forward / backward); seq: use the sequential chain
+    std::vector<int> pv;         // [rows]      pivot row offset of column j (0..KL)
+    std::vector<double> cfF;     // [rows][LF]  multipliers of column j (rows j+1..j+KL)
+    std::vector<double> cfB;     // [rows][LB]  U(j, j+1..j+KD), then 1 / U(j,j)
+    std::vector<double> cfC;     // [rows][LC]  Psi(j, 0..KD) (response to t), then Xi(j, 0..KL) (to delta)
+    std::vector<double> T;       // [SC][KL][KL] forward state transfer across chunk c
+    std::vector<double> Rm;      // [SC][KD][KD] first KD rows of Psi of chunk c
+    std::vector<double> W;       // [SC][MAX_DEPTH-1][KL][KL]  W_{c,d}, d = 2..  (products of T)
+    std::vector<double> V;       // [SC][MAX_DEPTH-1][KD][KD]  V_{c,d}, d = 2..  (products of Rm)
 };
-int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch,
+int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch, int group,
                      SweepPlan& plan);
 
 }  // namespace adsb

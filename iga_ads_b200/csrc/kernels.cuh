@@ -6,18 +6,21 @@
 
 namespace adsb {
 
-constexpr int SWEEP_CH = 33;  // columns per chunk held in registers by one thread
+constexpr int SWEEP_CH = 18;  // columns per chunk (one chunk per thread, held in registers)
+constexpr int SWEEP_RL = 2;   // lines per thread: they share every coefficient load and interleave for ILP
+constexpr int SWEEP_MAX_DEPTH_DEV = 6;  // == SWEEP_MAX_DEPTH of internal.hpp
 
-// One factorised band matrix, prepared by build_sweep_plan (host_setup.cpp); rows padded to S*CH.
+// One factorised band matrix, prepared by build_sweep_plan (host_setup.cpp).
 struct SweepFactor {
-    const double* Lm;    // [S*CH][KL]
-    const int* pv;       // [S*CH]
-    const double* Ut;    // [S*CH][KD]
-    const double* rinv;  // [S*CH]
-    const double* Phi;   // [S*CH][KL]
-    const double* Psi;   // [S*CH][KD]
-    const double* T;     // [S][KL][KL]
-    int n, S, KL, KD, piv;
+    const double* cfF;  // [rows][LF]  multipliers
+    const double* cfB;  // [rows][LB]  U rows + reciprocal diagonal
+    const double* cfC;  // [rows][LC]  Psi | Xi
+    const int* pv;      // [rows]
+    const double* T;    // [SC][KL][KL]
+    const double* Rm;   // [SC][KD][KD]
+    const double* W;    // [SC][MAX_DEPTH-1][KL][KL]
+    const double* V;    // [SC][MAX_DEPTH-1][KD][KD]
+    int n, ST, SC, KL, KD, piv, DF, DB, seq;
 };
 
 // Lines of one sweep.  A line is addressed as base(l0, l1) + off(j):
@@ -32,12 +35,13 @@ struct SweepGeom {
     long long s0_in, s0_out;
     long long s1_in, s1_out;
     int L0, L1;
-    int pitch;  // CONTIG: shared-memory row pitch in doubles (odd)
+    int pitch;  // CONTIG: shared-memory row pitch in doubles (even)
+    int bulk;   // CONTIG: rows are 16 B aligned on both sides -> TMA bulk copies
 };
 
 // returns cudaError_t as int
-int launch_sweep(const SweepFactor& F, const SweepGeom& G, bool contig, int NL, cudaStream_t st);
-int sweep_smem_bytes(const SweepFactor& F, bool contig, int NL, int pitch);
+int launch_sweep(const SweepFactor& F, const SweepGeom& G, bool contig, int NLt, cudaStream_t st);
+int sweep_smem_bytes(const SweepFactor& F, bool contig, int NLt, int pitch);
 
 // Collapsed right-hand side: rhs = sum over Kronecker terms of 1-D band operators applied to u.
 // op[d] points at coefficient rows [n_d][2p+1] (row i holds A(i, i-p .. i+p), zero outside).
@@ -46,8 +50,8 @@ struct RhsOps {
     const double* Sx;  // stiffness
     const double* My;
     const double* Sy;
-    const double* Mz;
-    const double* Sz;
+    const double* MzT;  // column tables: row k holds A(k-p .. k+p, k) (what input plane k feeds)
+    const double* SzT;
     int p[3];
     int n[3];  // global extents
 };

@@ -27,12 +27,16 @@ namespace {
 constexpr int TX = 32;
 constexpr int TYB = 8;  // threads along y
 
+// One CTA: TX x (TYB*NPT) DOFs, marching along z.  NPT vertically adjacent outputs per thread.
 template <int P, int NPT, bool D3>
-__global__ void __launch_bounds__(TX* TYB) rhs_collapsed_kernel(const RhsOps ops, const RhsGeom g, int zseg) {
+__global__ void __launch_bounds__(TX* TYB, 2) rhs_collapsed_kernel(const RhsOps ops, const RhsGeom g, int zseg) {
     constexpr int W = 2 * P + 1;
     constexpr int TY = TYB * NPT;
     constexpr int UW = TX + 2 * P;         // raw tile width
     constexpr int UH = TY + 2 * P;         // raw tile height
+    constexpr int NTH = TX * TYB;
+    constexpr int NPF = (UH * UW + NTH - 1) / NTH;  // raw-tile elements per thread
+    constexpr int NXR = (UH + TYB - 1) / TYB;       // x-pass rows per thread
     __shared__ double U[UH][UW + 1];
     __shared__ double Pf[UH][TX];
     __shared__ double Qf[UH][TX];
@@ -45,7 +49,20 @@ __global__ void __launch_bounds__(TX* TYB) rhs_collapsed_kernel(const RhsOps ops
     const int nx = ops.n[0], ny = ops.n[1];
     const bool xin = gx < g.out_lo[0] + g.out_n[0];
 
-    // coefficient rows of this thread's x (clamped: out-of-box lanes compute garbage nobody stores)
+    // where this thread's raw-tile elements live (fixed for the whole march); -1: outside the domain
+    int pf_off[NPF];
+    int pf_sm[NPF];
+#pragma unroll
+    for (int k = 0; k < NPF; ++k) {
+        const int idx = tid + k * NTH;
+        const int r = idx / UW, c = idx - r * UW;
+        const int yy = y0 - P + r, xx = x0 - P + c;
+        const bool ok = idx < UH * UW && xx >= 0 && xx < nx && yy >= 0 && yy < ny;
+        pf_off[k] = ok ? (int) ((xx - g.in_lo[0]) * g.si[0] + (yy - g.in_lo[1]) * g.si[1]) : -1;
+        pf_sm[k] = idx < UH * UW ? r * (UW + 1) + c : -1;
+    }
+
+    // coefficient rows of this thread's x and y's (clamped: out-of-box lanes compute garbage nobody stores)
     double kx[W], mx[W];
     {
         const int gxc = min(gx, nx - 1);
@@ -60,7 +77,7 @@ __global__ void __launch_bounds__(TX* TYB) rhs_collapsed_kernel(const RhsOps ops
     bool yin[NPT];
 #pragma unroll
     for (int r = 0; r < NPT; ++r) {
-        const int gy = y0 + ty + r * TYB;
+        const int gy = y0 + ty * NPT + r;
         yin[r] = gy < g.out_lo[1] + g.out_n[1];
         const int gyc = min(gy, ny - 1);
 #pragma unroll
@@ -70,16 +87,27 @@ __global__ void __launch_bounds__(TX* TYB) rhs_collapsed_kernel(const RhsOps ops
         }
     }
 
-    double Gw[NPT][D3 ? W : 1], Hw[NPT][D3 ? W : 1];
+    // acc[r][d]: partial sums of the outputs at planes kin-2P+d .. (scatter form of the z product)
+    double acc[NPT][D3 ? W : 1];
 #pragma unroll
     for (int r = 0; r < NPT; ++r)
 #pragma unroll
-        for (int m = 0; m < (D3 ? W : 1); ++m) Gw[r][m] = Hw[r][m] = 0.0;
+        for (int m = 0; m < (D3 ? W : 1); ++m) acc[r][m] = 0.0;
 
     const int nz = D3 ? ops.n[2] : 1;
     const int zs = D3 ? g.out_lo[2] + blockIdx.z * zseg : 0;
     const int ze = D3 ? min(zs + zseg, g.out_lo[2] + g.out_n[2]) : 1;
     const int kb = D3 ? zs - P : 0, ke = D3 ? ze + P : 1;
+    double* Uflat = &U[0][0];
+
+    double pf[NPF];
+    auto prefetch = [&](int k) {
+        const bool ok = k >= 0 && k < nz && k < ke;
+        const double* src = g.in + (long long) (k - g.in_lo[2]) * g.si[2];
+#pragma unroll
+        for (int q = 0; q < NPF; ++q) pf[q] = (ok && pf_off[q] >= 0) ? __ldg(src + pf_off[q]) : 0.0;
+    };
+    prefetch(kb);
 
     for (int kin = kb; kin < ke; ++kin) {
         const bool plane_ok = kin >= 0 && kin < nz;  // uniform
@@ -87,90 +115,96 @@ __global__ void __launch_bounds__(TX* TYB) rhs_collapsed_kernel(const RhsOps ops
 #pragma unroll
         for (int r = 0; r < NPT; ++r) Gn[r] = Hn[r] = 0.0;
         if (plane_ok) {
-            const double* src = g.in + (long long) (kin - g.in_lo[2]) * g.si[2];
-            for (int idx = tid; idx < UH * UW; idx += TX * TYB) {
-                const int r = idx / UW, c = idx - r * UW;
-                const int yy = y0 - P + r, xx = x0 - P + c;
-                double val = 0.0;
-                if (xx >= 0 && xx < nx && yy >= 0 && yy < ny)
-                    val = src[(long long) (xx - g.in_lo[0]) * g.si[0] + (long long) (yy - g.in_lo[1]) * g.si[1]];
-                U[r][c] = val;
-            }
-            __syncthreads();
-            for (int r = ty; r < UH; r += TYB) {
-                double a = 0.0, b = 0.0;
 #pragma unroll
-                for (int m = 0; m < W; ++m) {
-                    const double uv = U[r][tx + m];
-                    a = fma(kx[m], uv, a);
-                    b = fma(mx[m], uv, b);
+            for (int q = 0; q < NPF; ++q)
+                if (pf_sm[q] >= 0) Uflat[pf_sm[q]] = pf[q];
+            __syncthreads();
+            prefetch(kin + 1);
+#pragma unroll
+            for (int q = 0; q < NXR; ++q) {
+                const int r = ty + q * TYB;
+                if (r < UH) {
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int m = 0; m < W; ++m) {
+                        const double uv = U[r][tx + m];
+                        a = fma(kx[m], uv, a);
+                        b = fma(mx[m], uv, b);
+                    }
+                    Pf[r][tx] = a;
+                    Qf[r][tx] = b;
                 }
-                Pf[r][tx] = a;
-                Qf[r][tx] = b;
             }
             __syncthreads();
+            double pc[NPT + 2 * P], qc[NPT + 2 * P];
+#pragma unroll
+            for (int m = 0; m < NPT + 2 * P; ++m) {
+                pc[m] = Pf[ty * NPT + m][tx];
+                qc[m] = Qf[ty * NPT + m][tx];
+            }
 #pragma unroll
             for (int r = 0; r < NPT; ++r) {
-                const int yl = ty + r * TYB;
                 double gg = 0.0, hh = 0.0;
 #pragma unroll
                 for (int m = 0; m < W; ++m) {
-                    const double pv = Pf[yl + m][tx], qv = Qf[yl + m][tx];
-                    gg = fma(my[r][m], pv, gg);
-                    gg = fma(sy[r][m], qv, gg);
-                    hh = fma(my[r][m], qv, hh);
+                    gg = fma(my[r][m], pc[r + m], gg);
+                    gg = fma(sy[r][m], qc[r + m], gg);
+                    hh = fma(my[r][m], qc[r + m], hh);
                 }
                 Gn[r] = gg;
                 Hn[r] = -g.beta[2] * hh;
             }
+        } else {
+            prefetch(kin + 1);
         }
         if (D3) {
+            if (plane_ok) {
+                // column kin of Mz / Sz: entry d multiplies into output plane kin - P + d ... kin + P
+                double cm[W], cs[W];
 #pragma unroll
-            for (int r = 0; r < NPT; ++r) {
-#pragma unroll
-                for (int m = 0; m < W - 1; ++m) {
-                    Gw[r][m] = Gw[r][m + 1];
-                    Hw[r][m] = Hw[r][m + 1];
+                for (int d = 0; d < W; ++d) {
+                    cm[d] = ops.MzT[kin * W + d];
+                    cs[d] = ops.SzT[kin * W + d];
                 }
-                Gw[r][W - 1] = Gn[r];
-                Hw[r][W - 1] = Hn[r];
+#pragma unroll
+                for (int r = 0; r < NPT; ++r)
+#pragma unroll
+                    for (int d = 0; d < W; ++d) {
+                        acc[r][d] = fma(cm[d], Gn[r], acc[r][d]);
+                        acc[r][d] = fma(cs[d], Hn[r], acc[r][d]);
+                    }
             }
-            const int kout = kin - P;
+            const int kout = kin - P;  // complete now: every input plane <= kout + P has been added
             if (kout >= zs && kout < ze) {
-                double mz[W], sz[W];
-#pragma unroll
-                for (int m = 0; m < W; ++m) {
-                    mz[m] = ops.Mz[kout * W + m];
-                    sz[m] = ops.Sz[kout * W + m];
-                }
 #pragma unroll
                 for (int r = 0; r < NPT; ++r) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int m = 0; m < W; ++m) {
-                        acc = fma(mz[m], Gw[r][m], acc);
-                        acc = fma(sz[m], Hw[r][m], acc);
-                    }
                     if (xin && yin[r]) {
-                        const int gy = y0 + ty + r * TYB;
+                        const int gy = y0 + ty * NPT + r;
                         const long long o = (long long) (gx - g.out_lo[0]) * g.so[0] +
                                             (long long) (gy - g.out_lo[1]) * g.so[1] +
                                             (long long) (kout - g.out_lo[2]) * g.so[2];
-                        if (g.forcing) acc = fma(g.gamma, g.forcing[o], acc);
-                        g.out[o] = acc;
+                        double val = acc[r][0];
+                        if (g.forcing) val = fma(g.gamma, g.forcing[o], val);
+                        __stcs(g.out + o, val);
                     }
                 }
+            }
+#pragma unroll
+            for (int r = 0; r < NPT; ++r) {
+#pragma unroll
+                for (int d = 0; d < W - 1; ++d) acc[r][d] = acc[r][d + 1];
+                acc[r][W - 1] = 0.0;
             }
         } else {
 #pragma unroll
             for (int r = 0; r < NPT; ++r) {
                 if (xin && yin[r]) {
-                    const int gy = y0 + ty + r * TYB;
+                    const int gy = y0 + ty * NPT + r;
                     const long long o = (long long) (gx - g.out_lo[0]) * g.so[0] +
                                         (long long) (gy - g.out_lo[1]) * g.so[1];
-                    double acc = Gn[r];
-                    if (g.forcing) acc = fma(g.gamma, g.forcing[o], acc);
-                    g.out[o] = acc;
+                    double val = Gn[r];
+                    if (g.forcing) val = fma(g.gamma, g.forcing[o], val);
+                    __stcs(g.out + o, val);
                 }
             }
         }

@@ -203,10 +203,12 @@ int adsb_rhs_view(adsb_ctx* ctx, const adsb_form* form, const double* in, const 
 
 /* ---- introspection (used by the CPU test-suite to check the substitution plan without a GPU)
  * Builds the chunked-substitution plan of a factor exactly as adsb_set_axis_factor does and copies
- * it out.  dims[6] = {KL, KD, piv, CH, S, rows=S*CH}; arrays sized rows*KL (Lm, Phi), rows (pv,
- * rinv), rows*KD (Ut, Psi), S*KL*KL (T); any output pointer may be NULL. */
+ * it out.  dims[16] = {KL, KD, piv, CH, R, SC, ST, rows, LF, LB, LC, DF, DB, seq, MAX_DEPTH, 0};
+ * arrays: pv[rows], cfF[rows*LF], cfB[rows*LB], cfC[rows*LC], T[SC*KL*KL], Rm[SC*KD*KD],
+ * W[SC*(MAX_DEPTH-1)*KL*KL], V[SC*(MAX_DEPTH-1)*KD*KD]; any output pointer may be NULL. */
 int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int* dims,
-                    double* Lm, int* pv, double* Ut, double* rinv, double* Phi, double* Psi, double* T);
+                    int* pv, double* cfF, double* cfB, double* cfC, double* T, double* Rm, double* W,
+                    double* V);
 
 #ifdef __cplusplus
 }

@@ -86,62 +86,75 @@ def get_plan(lu, ipiv, kl, ku):
     lu = np.ascontiguousarray(lu)
     ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
     n, ldab = lu.shape
-    dims = np.zeros(6, dtype=np.int32)
+    dims = np.zeros(16, dtype=np.int32)
     none = None
-    _lib.check(lib.adsb_sweep_plan(n, kl, ku, ldab, _lib.d_(lu), _lib.i_(ipiv), _lib.i_(dims), none, none,
+    _lib.check(lib.adsb_sweep_plan(n, kl, ku, ldab, _lib.d_(lu), _lib.i_(ipiv), _lib.i_(dims), none, none, none,
                                    none, none, none, none, none))
-    KL, KD, piv, CH, S, rows = (int(v) for v in dims)
-    P = dict(KL=KL, KD=KD, piv=piv, CH=CH, S=S, n=n, Lm=np.zeros((rows, KL)), pv=np.zeros(rows, dtype=np.int32),
-             Ut=np.zeros((rows, KD)), rinv=np.zeros(rows), Phi=np.zeros((rows, KL)), Psi=np.zeros((rows, KD)),
-             T=np.zeros((S, KL, KL)))
-    _lib.check(lib.adsb_sweep_plan(n, kl, ku, ldab, _lib.d_(lu), _lib.i_(ipiv), _lib.i_(dims), _lib.d_(P["Lm"]),
-                                   _lib.i_(P["pv"]), _lib.d_(P["Ut"]), _lib.d_(P["rinv"]), _lib.d_(P["Phi"]),
-                                   _lib.d_(P["Psi"]), _lib.d_(P["T"])))
+    KL, KD, piv, CH, R, SC, ST, rows, LF, LB, LC, DF, DB, seq, MD, _ = (int(v) for v in dims)
+    P = dict(KL=KL, KD=KD, piv=piv, CH=CH, R=R, SC=SC, ST=ST, rows=rows, DF=DF, DB=DB, seq=seq, MD=MD, n=n,
+             pv=np.zeros(rows, dtype=np.int32), cfF=np.zeros((rows, LF)), cfB=np.zeros((rows, LB)),
+             cfC=np.zeros((rows, LC)), T=np.zeros((SC, KL, KL)), Rm=np.zeros((SC, KD, KD)),
+             W=np.zeros((SC, MD - 1, KL, KL)), V=np.zeros((SC, MD - 1, KD, KD)))
+    _lib.check(lib.adsb_sweep_plan(n, kl, ku, ldab, _lib.d_(lu), _lib.i_(ipiv), _lib.i_(dims), _lib.i_(P["pv"]),
+                                   _lib.d_(P["cfF"]), _lib.d_(P["cfB"]), _lib.d_(P["cfC"]), _lib.d_(P["T"]),
+                                   _lib.d_(P["Rm"]), _lib.d_(P["W"]), _lib.d_(P["V"])))
     return P
 
 
-def emulate_chunked_sweep(P, b):
-    """numpy transcription of sweep_kernel's five phases for one line (tests only)."""
-    KL, KD, CH, S, n = P["KL"], P["KD"], P["CH"], P["S"], P["n"]
-    bp = np.zeros(S * CH + KL)
+def emulate_chunked_sweep(P, b, force_seq=False):
+    """numpy transcription of sweep_kernel's phases for one line (tests only)."""
+    KL, KD, CH, SC, n = P["KL"], P["KD"], P["CH"], P["SC"], P["n"]
+    Lm, Ut, rinv = P["cfF"][:, :KL], P["cfB"][:, :KD], P["cfB"][:, KD]
+    Psi, Xi = P["cfC"][:, :KD], P["cfC"][:, KD:KD + KL]
+    bp = np.zeros(SC * CH + KL)
     bp[:n] = b
-    v = np.zeros((S, CH + KL))
-    fst = np.zeros((S, KL))
-    for s in range(S):                                  # F1
-        j0 = s * CH
-        v[s] = bp[j0:j0 + CH + KL]
-        o = v[s, CH:].copy()
+    v = np.zeros((SC, CH + KL))
+    Dl = np.zeros((SC, KL))
+    for c in range(SC):                                 # F1 + B1, local
+        j0 = c * CH
+        v[c] = bp[j0:j0 + CH + KL]
+        o = v[c, CH:].copy()
         for i in range(CH):
             t = P["pv"][j0 + i]
             if t:
-                v[s, i], v[s, i + t] = v[s, i + t], v[s, i]
+                v[c, i], v[c, i + t] = v[c, i + t], v[c, i]
             for r in range(1, KL + 1):
-                v[s, i + r] -= P["Lm"][j0 + i, r - 1] * v[s, i]
-        fst[s] = v[s, CH:] - o
-    d = np.zeros(KL)                                    # F2
-    delta = np.zeros((S, KL))
-    for s in range(S - 1):
-        d = fst[s] + P["T"][s] @ d
-        delta[s + 1] = d
-    bst = np.zeros((S, KD))
-    for s in range(S):                                  # B1
-        j0 = s * CH
+                v[c, i + r] -= Lm[j0 + i, r - 1] * v[c, i]
+        Dl[c] = v[c, CH:] - o
         for i in range(CH - 1, -1, -1):
-            acc = v[s, i] + P["Phi"][j0 + i] @ delta[s]
+            acc = v[c, i]
             for k in range(KD, 0, -1):
                 if i + k < CH:
-                    acc -= P["Ut"][j0 + i, k - 1] * v[s, i + k]
-            v[s, i] = acc * P["rinv"][j0 + i]
-        bst[s] = v[s, :KD]
-    t = np.zeros(KD)                                    # B2
-    tin = np.zeros((S, KD))
-    for s in range(S - 1, 0, -1):
-        t = bst[s] + P["Psi"][s * CH:s * CH + KD] @ t
-        tin[s - 1] = t
-    x = np.zeros(S * CH)
-    for s in range(S):                                  # B3
-        j0 = s * CH
-        x[j0:j0 + CH] = v[s, :CH] + P["Psi"][j0:j0 + CH] @ tin[s]
+                    acc -= Ut[j0 + i, k - 1] * v[c, i + k]
+            v[c, i] = acc * rinv[j0 + i]
+    seq = bool(P["seq"]) or force_seq
+    delta = np.zeros((SC, KL))                          # S1
+    if seq:
+        for c in range(SC - 1):
+            delta[c + 1] = Dl[c] + P["T"][c] @ delta[c]
+    else:
+        for c in range(1, SC):
+            delta[c] = Dl[c - 1]
+            for d in range(2, P["DF"] + 1):
+                if c - d >= 0:
+                    delta[c] += P["W"][c, d - 2] @ Dl[c - d]
+    X = np.zeros((SC, KD))
+    for c in range(SC):
+        X[c] = v[c, :KD] + Xi[c * CH:c * CH + KD] @ delta[c]
+    tin = np.zeros((SC, KD))                            # S2
+    if seq:
+        for c in range(SC - 1, 0, -1):
+            tin[c - 1] = X[c] + P["Rm"][c] @ tin[c]
+    else:
+        for c in range(SC - 1):
+            tin[c] = X[c + 1]
+            for d in range(2, P["DB"] + 1):
+                if c + d < SC:
+                    tin[c] += P["V"][c, d - 2] @ X[c + d]
+    x = np.zeros(SC * CH)
+    for c in range(SC):                                 # B3
+        j0 = c * CH
+        x[j0:j0 + CH] = v[c, :CH] + Psi[j0:j0 + CH] @ tin[c] + Xi[j0:j0 + CH] @ delta[c]
     return x[:n]
 
 
@@ -158,12 +171,13 @@ def test_chunked_plan_is_dgbtrs(oracle, p, ne, kind, h, fix):
     ab = ads.matrix_1d(kind, p, ne, h=h, fix=fix)
     lu, piv = ads.band_factorize(ab, p, p)
     P = get_plan(lu, piv, p, p)
-    assert P["KL"] >= p and P["S"] == -(-(ne + p) // P["CH"])
+    assert P["KL"] >= p and P["SC"] * P["CH"] >= ne + p and P["SC"] == P["ST"] * P["R"]
     rng = np.random.default_rng(p * 100 + ne)
     b = rng.standard_normal(ne + p)
     want = oracle.solve_factorized(lu, piv, p, p, b)
-    got = emulate_chunked_sweep(P, b)
-    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13, (P["piv"], P["KL"], P["KD"])
+    for force_seq in (False, True):
+        got = emulate_chunked_sweep(P, b, force_seq)
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13, (P["piv"], P["KL"], P["KD"], P["seq"])
 
 
 def test_plan_covers_pivoting_and_plain_variants():
