@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -134,9 +135,18 @@ struct StageTimer {
     }
 };
 
+int sweep_max_threads() {  // tuning knob (threads per CTA of the sweep kernel)
+    static int v = [] {
+        const char* e = getenv("ADSB_SWEEP_THREADS");
+        int t = e ? atoi(e) : 512;
+        return t < 32 ? 32 : (t > 512 ? 512 : t);
+    }();
+    return v;
+}
+
 int pick_nl(int SC) {  // lanes per CTA (each thread carries SWEEP_RL lines)
     int nl = 32;
-    while (nl > 2 && nl * SC > 512) nl >>= 1;
+    while (nl > 2 && nl * SC > sweep_max_threads()) nl >>= 1;
     return nl;
 }
 

@@ -102,6 +102,11 @@ def main():
         prob[tag + "_syn_steps"] = np.array([steps], dtype=np.int64)
         u1, _ = r.run(name, p, ne, dt, 1, u0=u0)
         prob[tag + "_syn_step1"] = u1
+        # noise floor of the comparison: how far the REFERENCE's own one-step result moves when
+        # every input coefficient is changed by one unit in the last place (random direction)
+        sgn = np.random.default_rng(11).choice([-1.0, 1.0], size=u0.size)
+        u1p, _ = r.run(name, p, ne, dt, 1, u0=np.nextafter(u0, u0 + sgn))
+        prob[tag + "_ulp_floor"] = np.array([np.linalg.norm(u1p - u1) / np.linalg.norm(u1)])
         nsub = 2 if name == "implicit_2d" else 3 if name == "implicit_3d" else 1
         for s in range(1, nsub + 1):
             rhs, _ = r.run(name, p, ne, dt, 1, u0=u0, stage=s)

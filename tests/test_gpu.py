@@ -15,6 +15,16 @@ pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-12
 TOL_100 = 1e-10
+# Tiny / high-degree meshes are so ill conditioned that the REFERENCE's own one-step result moves by
+# more than 1e-14 when its input is changed by one ulp (tests/golden: *_ulp_floor, measured with the
+# compiled reference).  Its element-order quadrature sum carries ~10-60 ulp of rounding of its own
+# (DESIGN.md "Parity"), which no other summation order can reproduce, so where 64 x floor exceeds
+# 1e-12 that is the tolerance.  Every BASELINE.json configuration stays on the plain 1e-12 bar.
+FLOOR_ULPS = 64
+
+
+def step_tol(g, tag):
+    return max(TOL_STEP, FLOOR_ULPS * float(g[tag + "_ulp_floor"][0]))
 
 
 def make_ctx(shape, mats, kl, ku):
@@ -141,11 +151,11 @@ def test_rhs_and_steps_vs_reference_golden(golden):
             assert rel_l2(ctx.download(U), g[f"{tag}_rhs{s}"]) < 1e-13, (tag, s)
         sim.set_state(u0)
         sim.advance(1)
-        assert rel_l2(sim.state(), g[tag + "_syn_step1"]) < TOL_STEP, tag
+        assert rel_l2(sim.state(), g[tag + "_syn_step1"]) < step_tol(g, tag), tag
         steps = int(g[tag + "_syn_steps"][0])
         sim.set_state(u0)
         sim.advance(steps)
-        assert rel_l2(sim.state(), g[tag + "_syn"]) < steps * TOL_STEP, tag
+        assert rel_l2(sim.state(), g[tag + "_syn"]) < steps * step_tol(g, tag), tag
 
 
 def test_heat3d_100_steps_vs_reference_golden(golden):
@@ -170,7 +180,13 @@ def test_one_step_vs_oracle(oracle, name, p, ne, dt):
     sim.set_state(u0)
     sim.advance(1)
     want, _ = oracle.run(name, p, ne, dt, 1, u0=u0)
-    assert rel_l2(sim.state(), want) < TOL_STEP, name
+    # one-ulp sensitivity of the oracle's own step (see FLOOR_ULPS above); 1e-12 wherever it allows
+    sgn = np.random.default_rng(11).choice([-1.0, 1.0], size=u0.size)
+    moved, _ = oracle.run(name, p, ne, dt, 1, u0=np.nextafter(u0, u0 + sgn))
+    tol = max(TOL_STEP, FLOOR_ULPS * rel_l2(moved, want))
+    if p <= 3:
+        assert tol < 1e-11, "p <= 3 cases stay near the plain bar"
+    assert rel_l2(sim.state(), want) < tol, (name, tol)
 
 
 def test_heat2d_100_steps_vs_oracle(oracle):
