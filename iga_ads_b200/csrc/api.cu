@@ -29,8 +29,7 @@ struct AxisData {
     std::vector<double> bt, xq, w, J;  // host copies (layout of adsb_basis_tables)
     double* d_M = nullptr;             // [n][2p+1] Gram rows
     double* d_S = nullptr;             // [n][2p+1] stiffness rows
-    double* d_MT = nullptr;            // [n][2p+1] Gram columns: row k holds A(k-p..k+p, k)
-    double* d_ST = nullptr;
+    double* d_MST = nullptr;           // [n+2p][2][2p+2] Gram | stiffness columns A(k-p..k+p, k) in row k+p
     double* d_bt = nullptr;            // device copy of bt
     double* d_xq = nullptr;
     double* d_wJ = nullptr;            // [elements][q] w[k]*J[e]
@@ -245,8 +244,7 @@ int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view&
     ops.Sx = c->ax[0].d_S;
     ops.My = c->ax[1].d_M;
     ops.Sy = c->ax[1].d_S;
-    ops.MzT = c->ndim == 3 ? c->ax[2].d_MT : nullptr;
-    ops.SzT = c->ndim == 3 ? c->ax[2].d_ST : nullptr;
+    ops.MSzT = c->ndim == 3 ? c->ax[2].d_MST : nullptr;
     RhsGeom g{};
     g.in = in;
     g.out = out;
@@ -339,8 +337,7 @@ int adsb_destroy(adsb_ctx* c) {
     for (auto& a : c->ax) {
         cudaFree(a.d_M);
         cudaFree(a.d_S);
-        cudaFree(a.d_MT);
-        cudaFree(a.d_ST);
+        cudaFree(a.d_MST);
         cudaFree(a.d_bt);
         cudaFree(a.d_xq);
         cudaFree(a.d_wJ);
@@ -395,9 +392,8 @@ int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int 
     std::vector<double> ab((size_t) (3 * p + 1) * a.n), rows;
     cudaFree(a.d_M);
     cudaFree(a.d_S);
-    cudaFree(a.d_MT);
-    cudaFree(a.d_ST);
-    a.d_MT = a.d_ST = nullptr;
+    cudaFree(a.d_MST);
+    a.d_MST = nullptr;
     cudaFree(a.d_bt);
     cudaFree(a.d_xq);
     cudaFree(a.d_wJ);
@@ -405,15 +401,20 @@ int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int 
     cudaFree(a.d_J);
     a.d_M = a.d_S = a.d_bt = a.d_xq = a.d_wJ = a.d_w = a.d_J = nullptr;
     if (int rc = matrix_from_tables(0, 0.0, p, elements, q, ders, b_flat, w, J, ab.data())) return rc;
+    const int W = 2 * p + 1, WP = W + 1;
+    std::vector<double> mst((size_t) (a.n + 2 * p) * 2 * WP, 0.0);  // p zero rows on both sides
     rows_from_band(a.n, p, ab, rows);
     if (int rc = upload_vec(rows, 0, &a.d_M, nullptr)) return rc;
     cols_from_band(a.n, p, ab, rows);
-    if (int rc = upload_vec(rows, 0, &a.d_MT, nullptr)) return rc;
+    for (int k = 0; k < a.n; ++k)
+        for (int d = 0; d < W; ++d) mst[(size_t) (k + p) * 2 * WP + d] = rows[(size_t) k * W + d];
     if (int rc = matrix_from_tables(1, 0.0, p, elements, q, ders, b_flat, w, J, ab.data())) return rc;
     rows_from_band(a.n, p, ab, rows);
     if (int rc = upload_vec(rows, 0, &a.d_S, nullptr)) return rc;
     cols_from_band(a.n, p, ab, rows);
-    if (int rc = upload_vec(rows, 0, &a.d_ST, nullptr)) return rc;
+    for (int k = 0; k < a.n; ++k)
+        for (int d = 0; d < W; ++d) mst[(size_t) (k + p) * 2 * WP + WP + d] = rows[(size_t) k * W + d];
+    if (int rc = upload_vec(mst, 0, &a.d_MST, nullptr)) return rc;
     if (int rc = upload_vec(a.bt, 0, &a.d_bt, nullptr)) return rc;
     if (int rc = upload_vec(a.xq, 0, &a.d_xq, nullptr)) return rc;
     std::vector<double> wJ((size_t) elements * q);

@@ -50,8 +50,8 @@ struct RhsOps {
     const double* Sx;  // stiffness
     const double* My;
     const double* Sy;
-    const double* MzT;  // column tables: row k holds A(k-p .. k+p, k) (what input plane k feeds)
-    const double* SzT;
+    const double* MSzT;  // column table [n+2p][2][2p+2]: row k+p holds Mz(k-p .. k+p, k), pad, Sz(k-p .. k+p, k), pad
+                         // (what input plane k feeds into output planes k-p .. k+p); p zero rows on both sides
     int p[3];
     int n[3];  // global extents
 };
