@@ -206,6 +206,19 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     G.pitch = F.n + (F.n & 1);
     if (G.pitch % 4 == 0) G.pitch += 2;  // pitch = 2 (mod 4): conflict-free 128-bit column access
     G.bulk = 0;
+    static const bool use_tile = [] {
+        const char* e = getenv("ADSB_SWEEP_TILE");
+        return !e || atoi(e) != 0;
+    }();
+    if (use_tile) {
+        StageTimer t(c, 1 + axis);
+        const int rc = launch_sweep_tile(F, G, contig, c->stream);
+        if (rc == 0) {
+            c->launches++;
+            return ADSB_OK;
+        }
+        if (rc > 0) return cuda_fail((cudaError_t) rc, "sweep tile kernel launch");
+    }
     int NL = pick_nl(F.SC);
     if (contig) {
         while (NL > 1 && sweep_smem_bytes(F, true, NL, G.pitch) > 200 * 1024) NL >>= 1;

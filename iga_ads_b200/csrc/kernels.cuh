@@ -39,6 +39,21 @@ struct SweepGeom {
     int bulk;   // CONTIG: rows are 16 B aligned on both sides -> TMA bulk copies
 };
 
+// Tile-streaming variant (kernels_sweep_tile.cu): persistent CTAs, TMA-fed shared-memory ring.
+struct SweepTileGeom {
+    const double* in;
+    double* out;
+    long long s0_in, s1_in, s0_out, s1_out;  // CONTIG: element strides of the two line indices
+    int L0, L1;        // lines: l0 in [0, L0) (x for the strided sweeps), l1 in [0, L1)
+    int nb0, ntiles;   // tiles of 16 lines along l0; nb0 * L1 tiles in all
+    int pitch;         // CONTIG: shared row pitch of a line (doubles)
+    int BR, NBX;       // STRIDED: TMA box rows, boxes per tile
+    int tile_doubles;  // shared-memory doubles per ring slot
+    int nbuf;          // ring depth
+};
+// 0: launched; -1: not eligible (caller falls back to launch_sweep); otherwise a cudaError_t
+int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cudaStream_t st);
+
 // returns cudaError_t as int
 int launch_sweep(const SweepFactor& F, const SweepGeom& G, bool contig, int NLt, cudaStream_t st);
 int sweep_smem_bytes(const SweepFactor& F, bool contig, int NLt, int pitch);

@@ -29,54 +29,11 @@
 #include <cstdint>
 
 #include "kernels.cuh"
+#include "sweep_core.cuh"
 
 namespace adsb {
 
 namespace {
-
-template <int N>
-__device__ __forceinline__ void ldrec(const double* __restrict__ p, double* o) {
-#pragma unroll
-    for (int k = 0; k + 1 < N; k += 2) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(p + k));
-        o[k] = t.x;
-        o[k + 1] = t.y;
-    }
-    if (N & 1) o[N - 1] = __ldg(p + N - 1);
-}
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes)
-                 : "memory");
-}
 
 // RL lines per thread share every coefficient load; NLt = blockDim.x lanes; a CTA owns NLt*RL lines.
 template <int KL, int KD, bool PIV, int CH, int RL, bool CONTIG>
@@ -169,209 +126,7 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepFactor F, cons
         }
     }
 
-    // ---------------------------------------------------------------- F1: local forward
-    double dl[RL][KL];
-#pragma unroll
-    for (int r = 0; r < RL; ++r)
-#pragma unroll
-        for (int k = 0; k < KL; ++k) dl[r][k] = v[r][CH + k];
-    {
-        const double* cf = F.cfF + (long long) j0 * LF;
-        const int* pv = F.pv + j0;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            double L[LF];
-            ldrec<LF>(cf + i * LF, L);
-            int t = 0;
-            if (PIV) t = __ldg(pv + i);
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                if (PIV) {
-#pragma unroll
-                    for (int q = 1; q <= KL; ++q) {
-                        if (t == q) {
-                            const double tmp = v[r][i];
-                            v[r][i] = v[r][i + q];
-                            v[r][i + q] = tmp;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 1; q <= KL; ++q) v[r][i + q] = fma(-L[q - 1], v[r][i], v[r][i + q]);
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RL; ++r)
-#pragma unroll
-        for (int k = 0; k < KL; ++k) {
-            dl[r][k] = v[r][CH + k] - dl[r][k];
-            fst[(c * KL + k) * NL + r * NLt + tx] = dl[r][k];
-        }
-
-    // ---------------------------------------------------------------- B1: local backward (zero right state)
-    {
-        const double* cf = F.cfB + (long long) j0 * LB;
-#pragma unroll
-        for (int i = CH - 1; i >= 0; --i) {
-            double Ub[LB];
-            ldrec<LB>(cf + i * LB, Ub);
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                double acc = v[r][i];
-#pragma unroll
-                for (int k = KD; k >= 1; --k)
-                    if (i + k < CH) acc = fma(-Ub[k - 1], v[r][i + k], acc);
-                v[r][i] = acc * Ub[KD];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---------------------------------------------------------------- S1: forward states, X_c
-    double dlt[RL][KL];
-    if (F.seq) {
-        if (c == 0) {
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                const int ln = r * NLt + tx;
-                double d[KL];
-#pragma unroll
-                for (int k = 0; k < KL; ++k) d[k] = 0.0;
-                for (int cc = 0; cc < SC - 1; ++cc) {
-                    const double* T = F.T + cc * KL * KL;
-                    double nd[KL];
-#pragma unroll
-                    for (int k = 0; k < KL; ++k) {
-                        double acc = fst[(cc * KL + k) * NL + ln];
-#pragma unroll
-                        for (int q = 0; q < KL; ++q) acc = fma(__ldg(T + k * KL + q), d[q], acc);
-                        nd[k] = acc;
-                    }
-#pragma unroll
-                    for (int k = 0; k < KL; ++k) {
-                        d[k] = nd[k];
-                        fst[(cc * KL + k) * NL + ln] = nd[k];  // now delta_{cc+1}
-                    }
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < RL; ++r)
-#pragma unroll
-            for (int k = 0; k < KL; ++k) dlt[r][k] = (c > 0) ? fst[((c - 1) * KL + k) * NL + r * NLt + tx] : 0.0;
-    } else {
-#pragma unroll
-        for (int r = 0; r < RL; ++r)
-#pragma unroll
-            for (int k = 0; k < KL; ++k) dlt[r][k] = (c > 0) ? fst[((c - 1) * KL + k) * NL + r * NLt + tx] : 0.0;
-        for (int d = 2; d <= F.DF && c - d >= 0; ++d) {
-            const double* W = F.W + ((long long) c * (MD - 1) + d - 2) * KL * KL;
-            double w[KL * KL];
-#pragma unroll
-            for (int q = 0; q < KL * KL; ++q) w[q] = __ldg(W + q);
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                double e[KL];
-#pragma unroll
-                for (int q = 0; q < KL; ++q) e[q] = fst[((c - d) * KL + q) * NL + r * NLt + tx];
-#pragma unroll
-                for (int k = 0; k < KL; ++k)
-#pragma unroll
-                    for (int q = 0; q < KL; ++q) dlt[r][k] = fma(w[k * KL + q], e[q], dlt[r][k]);
-            }
-        }
-    }
-    {
-        const double* cf = F.cfC + (long long) j0 * LC;
-#pragma unroll
-        for (int i = 0; i < KD; ++i) {
-            double xi[KL];
-#pragma unroll
-            for (int q = 0; q < KL; ++q) xi[q] = __ldg(cf + i * LC + KD + q);
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                double acc = v[r][i];
-#pragma unroll
-                for (int q = 0; q < KL; ++q) acc = fma(xi[q], dlt[r][q], acc);
-                bst[(c * KD + i) * NL + r * NLt + tx] = acc;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---------------------------------------------------------------- S2: backward states
-    double tt[RL][KD];
-    if (F.seq) {
-        if (c == 0) {
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                const int ln = r * NLt + tx;
-                double t[KD];
-#pragma unroll
-                for (int k = 0; k < KD; ++k) t[k] = 0.0;
-                for (int cc = SC - 1; cc >= 1; --cc) {
-                    const double* Rm = F.Rm + cc * KD * KD;
-                    double nt[KD];
-#pragma unroll
-                    for (int i = 0; i < KD; ++i) {
-                        double acc = bst[(cc * KD + i) * NL + ln];
-#pragma unroll
-                        for (int k = 0; k < KD; ++k) acc = fma(__ldg(Rm + i * KD + k), t[k], acc);
-                        nt[i] = acc;
-                    }
-#pragma unroll
-                    for (int i = 0; i < KD; ++i) {
-                        t[i] = nt[i];
-                        bst[(cc * KD + i) * NL + ln] = nt[i];  // now t_{cc-1}
-                    }
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < RL; ++r)
-#pragma unroll
-            for (int k = 0; k < KD; ++k) tt[r][k] = (c + 1 < SC) ? bst[((c + 1) * KD + k) * NL + r * NLt + tx] : 0.0;
-    } else {
-#pragma unroll
-        for (int r = 0; r < RL; ++r)
-#pragma unroll
-            for (int k = 0; k < KD; ++k) tt[r][k] = (c + 1 < SC) ? bst[((c + 1) * KD + k) * NL + r * NLt + tx] : 0.0;
-        for (int d = 2; d <= F.DB && c + d < SC; ++d) {
-            const double* V = F.V + ((long long) c * (MD - 1) + d - 2) * KD * KD;
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                double e[KD];
-#pragma unroll
-                for (int q = 0; q < KD; ++q) e[q] = bst[((c + d) * KD + q) * NL + r * NLt + tx];
-#pragma unroll
-                for (int k = 0; k < KD; ++k)
-#pragma unroll
-                    for (int q = 0; q < KD; ++q) tt[r][k] = fma(__ldg(V + k * KD + q), e[q], tt[r][k]);
-            }
-        }
-    }
-
-    // ---------------------------------------------------------------- B3: correct x
-    {
-        const double* cf = F.cfC + (long long) j0 * LC;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            double C[LC];
-            ldrec<LC>(cf + i * LC, C);
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                double acc = v[r][i];
-#pragma unroll
-                for (int k = 0; k < KD; ++k) acc = fma(C[k], tt[r][k], acc);
-#pragma unroll
-                for (int q = 0; q < KL; ++q) acc = fma(C[KD + q], dlt[r][q], acc);
-                v[r][i] = acc;
-            }
-        }
-    }
+    sweep_core<KL, KD, PIV, CH, RL>(F, v, fst, bst, c, tx, NLt, SC);
 
     // ---------------------------------------------------------------- store
     if (CONTIG) {

@@ -1,0 +1,336 @@
+// kernels_sweep_tile.cu -- K2, TMA-fed variant: persistent CTAs stream tiles of lines through a
+// shared-memory ring so that loads, the substitution and stores of neighbouring tiles overlap.
+//
+// Same algorithm and arithmetic as kernels_sweep.cu (sweep_core.cuh); only the data movement
+// differs.  One CTA per SM loops over tiles of NL = 16 lines:
+//   STRIDED sweeps (y, z; lanes along x): a tile is n rows x 16 x-values.  The TMA engine moves it
+//     with 3-D tensor-map copies (cp.async.bulk.tensor, boxes of 16 x <=256 rows; SASS UTMALDG /
+//     UTMASTG); rows past the end of the line are zero-filled on load and clipped on store.
+//   CONTIG sweep (x): a tile is 16 whole lines, one bulk copy (cp.async.bulk, UBLKCP) per line.
+// Ring of NBUF tiles: while the threads solve tile i out of shared memory (in place), tiles i+1 and
+// i+2 are landing and tile i-1 is draining.  A thread reads / writes its chunk with 128-bit shared
+// accesses at compile-time offsets -- no per-element address arithmetic, no LSU queue limits on
+// the bytes in flight.
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "sweep_core.cuh"
+
+namespace adsb {
+
+namespace {
+
+constexpr int MAX_NBUF = 3;
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_addr(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(smem_addr(src))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// Block = ncons consumer threads (NLt lanes x chunks, padded to whole warps) + one producer warp.
+template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
+__global__ void __launch_bounds__(288, 1)
+    sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G, const __grid_constant__ CUtensorMap tm_in,
+                      const __grid_constant__ CUtensorMap tm_out) {
+    constexpr int RL = SWEEP_RL, NLt = NL / RL;
+    constexpr int LF = KL + (KL & 1), LB = (KD + 1) + ((KD + 1) & 1), LC = (KD + KL) + ((KD + KL) & 1);
+    constexpr int MD = SWEEP_MAX_DEPTH_DEV;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int SC = F0.SC;
+    const int ncons = (int) blockDim.x - 32;
+    const int tid = threadIdx.x;
+    const int n = F0.n;
+    const int tile_doubles = G.tile_doubles;
+    const int rows = SC * CH + KL + KD;  // rows of the coefficient tables (build_sweep_plan)
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    double* fst = tiles + (size_t) G.nbuf * tile_doubles;  // [SC][KL][NL]
+    double* bst = fst + SC * KL * NL;                      // [SC][KD][NL]
+    double* s_cfF = bst + SC * KD * NL;
+    double* s_cfB = s_cfF + rows * LF;
+    double* s_cfC = s_cfB + rows * LB;
+    double* s_T = s_cfC + rows * LC;
+    double* s_Rm = s_T + SC * KL * KL;
+    double* s_W = s_Rm + SC * KD * KD;
+    double* s_V = s_W + SC * (MD - 1) * KL * KL;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_V + SC * (MD - 1) * KD * KD);
+    uint64_t* done = full + MAX_NBUF;
+
+    if (tid == 0) {
+        for (int b = 0; b < G.nbuf; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&done[b], 1);
+        }
+    }
+    // rows the TMA never writes stay zero for the whole kernel (chunks may read past the line end)
+    for (int i = tid; i < G.nbuf * tile_doubles; i += blockDim.x) tiles[i] = 0.0;
+    // the factor's tables: every tile of this persistent CTA uses them
+    for (int i = tid; i < rows * LF; i += blockDim.x) s_cfF[i] = F0.cfF[i];
+    for (int i = tid; i < rows * LB; i += blockDim.x) s_cfB[i] = F0.cfB[i];
+    for (int i = tid; i < rows * LC; i += blockDim.x) s_cfC[i] = F0.cfC[i];
+    for (int i = tid; i < SC * KL * KL; i += blockDim.x) s_T[i] = F0.T[i];
+    for (int i = tid; i < SC * KD * KD; i += blockDim.x) s_Rm[i] = F0.Rm[i];
+    for (int i = tid; i < SC * (MD - 1) * KL * KL; i += blockDim.x) s_W[i] = F0.W[i];
+    for (int i = tid; i < SC * (MD - 1) * KD * KD; i += blockDim.x) s_V[i] = F0.V[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int my_count = (G.ntiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+
+    if (tid >= ncons) {
+        // ------------------------------------------------------------------ producer warp
+        if (tid != ncons) return;
+        auto issue_load = [&](int i) {
+            const int t = blockIdx.x + i * gridDim.x;
+            const int bx = t % G.nb0, m = t / G.nb0;
+            const int b = i % G.nbuf;
+            double* dst = tiles + (size_t) b * tile_doubles;
+            if (CONTIG) {
+                const int lines = min(NL, G.L0 - bx * NL);
+                mbar_expect_tx(&full[b], (uint32_t) (lines * n * 8));
+                const double* src = G.in + (long long) (bx * NL) * G.s0_in + (long long) m * G.s1_in;
+                for (int ln = 0; ln < lines; ++ln)
+                    bulk_g2s(dst + ln * G.pitch, src + ln * G.s0_in, (uint32_t) (n * 8), &full[b]);
+            } else {
+                mbar_expect_tx(&full[b], (uint32_t) (G.NBX * G.BR * NL * 8));
+                for (int k = 0; k < G.NBX; ++k) tma_load_3d(dst + k * G.BR * NL, &tm_in, bx * NL, k * G.BR, m, &full[b]);
+            }
+        };
+        auto issue_store = [&](int i) {
+            const int t = blockIdx.x + i * gridDim.x;
+            const int bx = t % G.nb0, m = t / G.nb0;
+            const int b = i % G.nbuf;
+            const double* src = tiles + (size_t) b * tile_doubles;
+            if (CONTIG) {
+                const int lines = min(NL, G.L0 - bx * NL);
+                double* dst = G.out + (long long) (bx * NL) * G.s0_out + (long long) m * G.s1_out;
+                for (int ln = 0; ln < lines; ++ln) bulk_s2g(dst + ln * G.s0_out, src + ln * G.pitch, (uint32_t) (n * 8));
+            } else {
+                for (int k = 0; k < G.NBX; ++k) tma_store_3d(&tm_out, bx * NL, k * G.BR, m, src + k * G.BR * NL);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        };
+        for (int i = 0; i < G.nbuf - 1 && i < my_count; ++i) issue_load(i);
+        for (int j = 0; j < my_count; ++j) {
+            if (j + G.nbuf - 1 < my_count) {
+                // ring slot of tile j-1: reusable once its store has read shared memory
+                if (j >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue_load(j + G.nbuf - 1);
+            }
+            mbar_wait(&done[j % G.nbuf], (uint32_t) ((j / G.nbuf) & 1));
+            issue_store(j);
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    SweepFactor F = F0;
+    F.cfF = s_cfF;
+    F.cfB = s_cfB;
+    F.cfC = s_cfC;
+    F.T = s_T;
+    F.Rm = s_Rm;
+    F.W = s_W;
+    F.V = s_V;
+    const int tx = tid % NLt;
+    const int c = min(tid / NLt, SC - 1);  // padding threads shadow the last chunk (identical values)
+    const int j0 = c * CH;
+
+    for (int i = 0; i < my_count; ++i) {
+        const int b = i % G.nbuf;
+        double* tile = tiles + (size_t) b * tile_doubles;
+        mbar_wait(&full[b], (uint32_t) ((i / G.nbuf) & 1));
+
+        double v[RL][CH + KL];
+        bool act[RL];
+        if (CONTIG) {
+            const int t = blockIdx.x + i * gridDim.x;
+            const int lbase = (t % G.nb0) * NL;
+#pragma unroll
+            for (int r = 0; r < RL; ++r) {
+                act[r] = lbase + r * NLt + tx < G.L0;
+                const double* mine = tile + (r * NLt + tx) * G.pitch + j0;
+#pragma unroll
+                for (int q = 0; q < CH + KL; q += 2) {  // CH, KL even on this path; pitch and j0 even
+                    double2 t2 = make_double2(0.0, 0.0);
+                    if (act[r] && j0 + q < n) t2 = *reinterpret_cast<const double2*>(mine + q);
+                    v[r][q] = t2.x;
+                    v[r][q + 1] = (j0 + q + 1 < n) ? t2.y : 0.0;
+                }
+            }
+        } else {
+            const double* mine = tile + (size_t) j0 * NL + 2 * tx;
+#pragma unroll
+            for (int q = 0; q < CH + KL; ++q) {
+                const double2 t2 = *reinterpret_cast<const double2*>(mine + q * NL);
+                v[0][q] = t2.x;
+                v[1][q] = t2.y;
+            }
+        }
+
+        sweep_core<KL, KD, PIV, CH, RL, true>(F, v, fst, bst, c, tx, NLt, SC, ncons);
+
+        if (CONTIG) {
+#pragma unroll
+            for (int r = 0; r < RL; ++r) {
+                double* mine = tile + (r * NLt + tx) * G.pitch + j0;
+#pragma unroll
+                for (int q = 0; q < CH; q += 2) {
+                    if (act[r] && j0 + q + 1 < n)
+                        *reinterpret_cast<double2*>(mine + q) = make_double2(v[r][q], v[r][q + 1]);
+                    else if (act[r] && j0 + q < n)
+                        mine[q] = v[r][q];
+                }
+            }
+        } else {
+            double* mine = tile + (size_t) j0 * NL + 2 * tx;
+#pragma unroll
+            for (int q = 0; q < CH; ++q)
+                if (j0 + q < n) *reinterpret_cast<double2*>(mine + q * NL) = make_double2(v[0][q], v[1][q]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        sweep_sync(ncons);
+        if (tid == 0) mbar_arrive(&done[b]);
+    }
+}
+
+using tile_kern_t = void (*)(const SweepFactor, const SweepTileGeom, const CUtensorMap, const CUtensorMap);
+
+template <int P, bool PIV, int NL>
+tile_kern_t pick_mode(bool contig) {
+    constexpr int KD = PIV ? 2 * P : P;
+    return contig ? (tile_kern_t) sweep_tile_kernel<P, KD, PIV, SWEEP_CH, NL, true>
+                  : (tile_kern_t) sweep_tile_kernel<P, KD, PIV, SWEEP_CH, NL, false>;
+}
+
+template <int NL>
+tile_kern_t pick(int KL, bool piv, bool contig) {
+    switch (KL) {
+    case 1: return piv ? pick_mode<1, true, NL>(contig) : pick_mode<1, false, NL>(contig);
+    case 2: return piv ? pick_mode<2, true, NL>(contig) : pick_mode<2, false, NL>(contig);
+    case 3: return piv ? pick_mode<3, true, NL>(contig) : pick_mode<3, false, NL>(contig);
+    case 4: return piv ? pick_mode<4, true, NL>(contig) : pick_mode<4, false, NL>(contig);
+    case 5: return piv ? pick_mode<5, true, NL>(contig) : pick_mode<5, false, NL>(contig);
+    default: return nullptr;
+    }
+}
+
+typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn_t encode_fn() {
+    static encode_fn_t fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (encode_fn_t) p;
+    }();
+    return fn;
+}
+
+// 3-D map over (x, sweep axis, other axis) with element strides (1, sj, s1); box NL x BR x 1
+bool make_map(CUtensorMap* m, const double* base, int L0, int n, int L1, long long sj, long long s1, int BR, int NL) {
+    encode_fn_t enc = encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t) L0, (cuuint64_t) n, (cuuint64_t) (L1 > 0 ? L1 : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t) sj * 8, (cuuint64_t) (L1 > 1 ? s1 : sj * n) * 8};
+    const cuuint32_t box[3] = {(cuuint32_t) NL, (cuuint32_t) BR, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*) base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+           CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// Returns cudaSuccess (0) when the tile kernel was launched, -1 when this sweep is not eligible (the
+// caller then uses the register-path kernel), or a CUDA error.
+int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cudaStream_t st) {
+    static const int NL = [] {
+        const char* e = getenv("ADSB_SWEEP_NL");
+        const int v = e ? atoi(e) : 16;
+        return v == 12 ? 12 : 16;
+    }();
+    const int NLt = NL / SWEEP_RL;
+    if (G.off_in || G.off_out) return -1;
+    const int ncons = (NLt * F.SC + 31) / 32 * 32;
+    if (ncons > 256) return -1;
+    if (contig && (SWEEP_CH % 2 || F.KL % 2)) return -1;  // the 128-bit chunk path needs even CH and KL
+    auto even = [](long long v) { return (v & 1) == 0; };
+    const bool ptr_ok = ((uintptr_t) G.in % 16 == 0) && ((uintptr_t) G.out % 16 == 0);
+    SweepTileGeom T{};
+    T.in = G.in;
+    T.out = G.out;
+    T.L0 = G.L0;
+    T.L1 = G.L1;
+    T.s0_in = G.s0_in;
+    T.s1_in = G.s1_in;
+    T.s0_out = G.s0_out;
+    T.s1_out = G.s1_out;
+    T.nb0 = (G.L0 + NL - 1) / NL;
+    T.ntiles = T.nb0 * G.L1;
+    const int rows_needed = F.SC * SWEEP_CH + F.KL;
+    CUtensorMap tm_in{}, tm_out{};
+    if (contig) {
+        if (!ptr_ok || !even(F.n) || !even(G.s0_in) || !even(G.s1_in) || !even(G.s0_out) || !even(G.s1_out)) return -1;
+        int pitch = rows_needed + (rows_needed & 1);
+        while (pitch % 16 != 2) pitch += 2;  // lanes 16 B apart modulo 128 B: conflict-free 128-bit chunk access
+        T.pitch = pitch;
+        T.tile_doubles = NL * pitch;
+    } else {
+        if (!ptr_ok || G.s0_in != 1 || G.s0_out != 1 || !even(G.sj_in) || !even(G.sj_out) ||
+            (G.L1 > 1 && (!even(G.s1_in) || !even(G.s1_out))))
+            return -1;
+        T.NBX = (F.n + 255) / 256;
+        T.BR = (F.n + T.NBX - 1) / T.NBX;
+        const int rows = T.NBX * T.BR > rows_needed ? T.NBX * T.BR : rows_needed;
+        T.tile_doubles = rows * NL;
+        if (!make_map(&tm_in, G.in, G.L0, F.n, G.L1, G.sj_in, G.s1_in, T.BR, NL)) return -1;
+        if (!make_map(&tm_out, G.out, G.L0, F.n, G.L1, G.sj_out, G.s1_out, T.BR, NL)) return -1;
+    }
+    T.tile_doubles = (T.tile_doubles + 15) & ~15;  // 128 B granules
+    const int LF = F.KL + (F.KL & 1), LB = (F.KD + 1) + ((F.KD + 1) & 1), LC = (F.KD + F.KL) + ((F.KD + F.KL) & 1);
+    const int rows = F.SC * SWEEP_CH + F.KL + F.KD;
+    const size_t fixed_doubles = (size_t) F.SC * (F.KL + F.KD) * NL + (size_t) rows * (LF + LB + LC) +
+                                 (size_t) F.SC * (F.KL * F.KL + F.KD * F.KD) * SWEEP_MAX_DEPTH_DEV;
+    const size_t fixed_bytes = fixed_doubles * 8 + 2 * MAX_NBUF * 8 + 64;
+    const size_t budget = 226 * 1024;
+    if (fixed_bytes + 2 * (size_t) T.tile_doubles * 8 > budget) return -1;
+    int nbuf = (int) ((budget - fixed_bytes) / ((size_t) T.tile_doubles * 8));
+    if (nbuf > MAX_NBUF) nbuf = MAX_NBUF;
+    T.nbuf = nbuf;
+    const size_t smem = (size_t) nbuf * T.tile_doubles * 8 + fixed_bytes;
+    tile_kern_t k = NL == 12 ? pick<12>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
+    if (!k) return -1;
+    cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    static int sms = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    dim3 block(ncons + 32, 1, 1);
+    dim3 grid(T.ntiles < sms ? T.ntiles : sms, 1, 1);
+    k<<<grid, block, smem, st>>>(F, T, tm_in, tm_out);
+    return (int) cudaGetLastError();
+}
+
+}  // namespace adsb
