@@ -35,12 +35,12 @@ class AdsbError(RuntimeError):
 class Form(ctypes.Structure):
     """adsb_form: rhs = alpha*(u,v) - sum_k beta[k]*(d_k u, d_k v) + gamma*F."""
     _fields_ = [("alpha", c_dbl), ("beta", c_dbl * 3), ("gamma", c_dbl), ("forcing_buf", c_int),
-                ("method", c_int)]
+                ("method", c_int), ("source", c_int)]
 
     @classmethod
-    def make(cls, alpha=1.0, beta=(0.0, 0.0, 0.0), gamma=0.0, forcing_buf=-1, method=RHS_COLLAPSED):
+    def make(cls, alpha=1.0, beta=(0.0, 0.0, 0.0), gamma=0.0, forcing_buf=-1, method=RHS_COLLAPSED, source=0):
         b = list(beta) + [0.0] * (3 - len(beta))
-        return cls(alpha, (c_dbl * 3)(*b), gamma, forcing_buf, method)
+        return cls(alpha, (c_dbl * 3)(*b), gamma, forcing_buf, method, source)
 
 
 class Substep(ctypes.Structure):

@@ -246,12 +246,79 @@ adsb_view local_view(const adsb_ctx* c) {
     return v;
 }
 
+int quad_axes(adsb_ctx* c, QuadAxes& A) {
+    A = QuadAxes{};
+    A.ndim = c->ndim;
+    for (int d = 0; d < c->ndim; ++d) {
+        const AxisData& a = c->ax[d];
+        if (!a.tables) return fail(ADSB_ESTATE, "axis tables not uploaded");
+        A.p[d] = a.p;
+        A.q[d] = a.q;
+        A.ne[d] = a.elements;
+        A.st[d] = (a.ders + 1) * (a.p + 1);
+        A.bt[d] = a.d_bt;
+        A.xq[d] = a.d_xq;
+        A.w[d] = a.d_w;
+        A.J[d] = a.d_J;
+    }
+    return ADSB_OK;
+}
+
+
+// General quadrature path: zero the out box, integrate every element that touches it, add gamma * F.
+int rhs_quadrature_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view& vi, const int* in_lo,
+                        const double* forcing, double* out, const adsb_view& vo, const int* out_lo) {
+    QuadAxes A;
+    if (int rc = quad_axes(c, A)) return rc;
+    RhsGeom g{};
+    g.in = in;
+    g.out = out;
+    g.forcing = nullptr;
+    int elo[3] = {0, 0, 0}, en[3] = {1, 1, 1}, on[3] = {1, 1, 1};
+    long long so[3] = {1, 0, 0};
+    for (int d = 0; d < 3; ++d) {
+        g.si[d] = vi.s[d];
+        g.so[d] = vo.s[d];
+        g.in_lo[d] = in_lo[d];
+        g.in_n[d] = vi.n[d];
+        g.out_lo[d] = out_lo[d];
+        g.out_n[d] = vo.n[d];
+        g.beta[d] = d < c->ndim ? f.beta[d] : 0.0;
+        so[d] = vo.s[d];
+        on[d] = d < c->ndim ? vo.n[d] : 1;
+        if (d < c->ndim) {
+            const int p = c->ax[d].p;
+            if (c->ax[d].q != p + 1 || c->ax[d].ders != 1)
+                return fail(ADSB_EINVAL, "compute_rhs(quadrature): needs quad_order = p + 1 and derivatives = 1");
+            elo[d] = std::max(0, out_lo[d] - p);
+            const int ehi = std::min(c->ax[d].elements - 1, out_lo[d] + vo.n[d] - 1);
+            en[d] = ehi - elo[d] + 1;
+            if (in_lo[d] > elo[d] || in_lo[d] + vi.n[d] < ehi + p + 1)
+                return fail(ADSB_EINVAL, "compute_rhs: input box lacks the p-wide halo of the output box");
+        }
+    }
+    g.alpha = f.alpha;
+    g.gamma = f.gamma;
+    if (f.source < 0 || f.source > 1) return fail(ADSB_EINVAL, "compute_rhs: unknown source");
+    StageTimer t(c, 0);
+    cudaError_t e = (cudaError_t) launch_zero_box(out, on, so, c->stream);
+    if (e == cudaSuccess) e = (cudaError_t) launch_rhs_quadrature(c->ndim, A, g, f.gamma != 0.0 ? f.source : 0, elo, en, c->stream);
+    c->launches += 2;
+    if (e == cudaSuccess && forcing && f.gamma != 0.0) {
+        e = (cudaError_t) launch_axpy_box(out, forcing, f.gamma, on, so, c->stream);
+        c->launches++;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "quadrature rhs kernels");
+    return ADSB_OK;
+}
+
 int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view& vi, const int* in_lo,
              const double* forcing, double* out, const adsb_view& vo, const int* out_lo) {
-    if (f.method != ADSB_RHS_COLLAPSED)
-        return fail(ADSB_EINVAL, "compute_rhs: only ADSB_RHS_COLLAPSED is built in this version");
+    if (f.method != ADSB_RHS_COLLAPSED && f.method != ADSB_RHS_QUADRATURE)
+        return fail(ADSB_EINVAL, "compute_rhs: unknown method");
     for (int d = 0; d < c->ndim; ++d)
         if (!c->ax[d].tables) return fail(ADSB_ESTATE, "compute_rhs: axis tables not uploaded");
+    if (f.method == ADSB_RHS_QUADRATURE) return rhs_quadrature_impl(c, f, in, vi, in_lo, forcing, out, vo, out_lo);
     RhsOps ops{};
     ops.Mx = c->ax[0].d_M;
     ops.Sx = c->ax[0].d_S;
@@ -541,7 +608,8 @@ int adsb_compute_rhs(adsb_ctx* c, const adsb_form* f, int src, int dst) {
     if (int rc = select_device(c)) return rc;
     if (int rc = ensure_buf(c, dst)) return rc;
     const double* forcing = nullptr;
-    if (f->gamma != 0.0) {
+    const bool pointwise_source = f->method == ADSB_RHS_QUADRATURE && f->source != 0 && f->forcing_buf < 0;
+    if (f->gamma != 0.0 && !pointwise_source) {
         if (f->forcing_buf < 0 || f->forcing_buf >= ADSB_MAX_BUFFERS || !c->buf[f->forcing_buf])
             return fail(ADSB_ESTATE, "compute_rhs: forcing buffer not allocated");
         forcing = c->buf[f->forcing_buf];
@@ -629,24 +697,6 @@ int adsb_stage_times(adsb_ctx* c, double* ms5) {
 }
 
 long long adsb_launch_count(adsb_ctx* c) { return c ? c->launches : 0; }
-
-static int quad_axes(adsb_ctx* c, QuadAxes& A) {
-    A = QuadAxes{};
-    A.ndim = c->ndim;
-    for (int d = 0; d < c->ndim; ++d) {
-        const AxisData& a = c->ax[d];
-        if (!a.tables) return fail(ADSB_ESTATE, "axis tables not uploaded");
-        A.p[d] = a.p;
-        A.q[d] = a.q;
-        A.ne[d] = a.elements;
-        A.st[d] = (a.ders + 1) * (a.p + 1);
-        A.bt[d] = a.d_bt;
-        A.xq[d] = a.d_xq;
-        A.w[d] = a.d_w;
-        A.J[d] = a.d_J;
-    }
-    return ADSB_OK;
-}
 
 int adsb_load_tensor(adsb_ctx* c, int source, int with_test_function, int dst) {
     if (!c) return fail(ADSB_EINVAL, "null context");

@@ -95,6 +95,14 @@ int launch_element_source(int src, const QuadAxes& A, double* G, const int elo[3
 int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int elo[3], const int en[3],
                    const int lo[3], const int n[3], cudaStream_t st);
 
+// General quadrature right-hand side (kernels_quadrhs.cu): elements [elo, elo+en) are integrated and
+// scattered (atomically) into the DOFs of g's out box, which must be zero on entry.  source: built-in
+// pointwise source added as gamma * f(x_q) * w * J to every local DOF (0: none).
+int launch_rhs_quadrature(int ndim, const QuadAxes& A, const RhsGeom& g, int source, const int elo[3], const int en[3],
+                          cudaStream_t st);
+int launch_zero_box(double* y, const int n[3], const long long s[3], cudaStream_t st);
+int launch_axpy_box(double* y, const double* x, double a, const int n[3], const long long s[3], cudaStream_t st);
+
 int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,
                      const double* values, cudaStream_t st);
 

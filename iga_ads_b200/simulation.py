@@ -341,7 +341,9 @@ class _scalability:
         self.x.fix_left()
         super().prepare_matrices()
         # time-independent load: dt * sum_q f(x_q) w J added to every DOF of the element
-        self._context().load_tensor(1, False, FORCING)
+        # (the quadrature method evaluates the source at the Gauss points itself)
+        if self.method == _lib.RHS_COLLAPSED:
+            self._context().load_tensor(1, False, FORCING)
 
     def before(self):
         self.prepare_matrices()
@@ -352,6 +354,8 @@ class _scalability:
     def substeps(self):
         dt = self.steps.dt
         beta = (dt,) * len(self.dims)
+        if self.method == _lib.RHS_QUADRATURE:
+            return [Substep.make(Form.make(1.0, beta, gamma=dt, method=self.method, source=1))]
         return [Substep.make(Form.make(1.0, beta, gamma=dt, forcing_buf=FORCING, method=self.method))]
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ADSB_ABI_VERSION 1
+#define ADSB_ABI_VERSION 2
 
 #define ADSB_OK 0
 #define ADSB_EINVAL (-1)     /* bad argument */
@@ -128,7 +128,9 @@ int adsb_set_plane(adsb_ctx* ctx, int buf, int axis, int idx, const double* valu
  * method ADSB_RHS_COLLAPSED applies the exactly pre-integrated 1-D quadrature operators
  * (sum factorisation carried through the quadrature sums; HBM-bound);
  * method ADSB_RHS_QUADRATURE evaluates u and grad u at every Gauss point and integrates against
- * the test functions by sum factorisation (general pointwise forms; FP64-bound). */
+ * the test functions by sum factorisation (general pointwise forms; FP64-bound); it zeroes dst and
+ * scatter-adds element contributions like zero(rhs) + update_global_rhs
+ * (include/ads/simulation/simulation_3d.hpp:140-145), so the summation order is not fixed. */
 #define ADSB_RHS_COLLAPSED 0
 #define ADSB_RHS_QUADRATURE 1
 typedef struct {
@@ -137,6 +139,9 @@ typedef struct {
     double gamma;    /* coefficient of the load tensor in `forcing_buf` (0: none) */
     int forcing_buf; /* managed buffer id holding F, or -1 */
     int method;      /* ADSB_RHS_COLLAPSED / ADSB_RHS_QUADRATURE */
+    int source;      /* ADSB_RHS_QUADRATURE only: built-in source f evaluated at the quadrature points and
+                        added as gamma*f(x_q)*w*J to every DOF of the element -- without the test function,
+                        as examples/scalability/test3d.hpp:86-88 does; 0 none, 1 the scalability forcing */
 } adsb_form;
 int adsb_compute_rhs(adsb_ctx* ctx, const adsb_form* form, int src_buf, int dst_buf);
 

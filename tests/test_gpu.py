@@ -158,6 +158,43 @@ def test_rhs_and_steps_vs_reference_golden(golden):
         assert rel_l2(sim.state(), g[tag + "_syn"]) < steps * step_tol(g, tag), tag
 
 
+def test_quadrature_method_vs_reference_golden(golden):
+    """ADSB_RHS_QUADRATURE (element-wise Gauss quadrature with sum factorisation, pointwise form and
+    source) on every example: each compute_rhs and one step against the compiled reference."""
+    g = golden["problems"]
+    for tag in _problem_tags(g):
+        pid, p, ne, ns = (int(v) for v in g[tag + "_meta"])
+        dt = float(g[tag + "_dt"][0])
+        sim = ads.PROBLEMS[NAMES[pid]](p, ne, ads.timesteps_config(1, dt), method=ads.RHS_QUADRATURE)
+        sim.prepare_matrices()
+        u0 = g[tag + "_u0"]
+        ctx = sim.ctx
+        for s, sub in enumerate(sim.substeps(), start=1):
+            assert sub.form.method == ads.RHS_QUADRATURE
+            ctx.upload(U_PREV, u0)
+            ctx.compute_rhs(sub.form, U_PREV, U)
+            assert rel_l2(ctx.download(U), g[f"{tag}_rhs{s}"]) < 1e-13, (tag, s)
+        sim.set_state(u0)
+        sim.advance(1)
+        assert rel_l2(sim.state(), g[tag + "_syn_step1"]) < step_tol(g, tag), tag
+
+
+def test_quadrature_matches_collapsed_at_128():
+    """the two right-hand-side kernels agree on a size with many CTAs (heat_3d p=2, 128^3)"""
+    p, ne, dt = 2, 128, 1e-7
+    outs = []
+    u0 = None
+    for method in (ads.RHS_COLLAPSED, ads.RHS_QUADRATURE):
+        sim = ads.heat_3d(p, ne, ads.timesteps_config(1, dt), method=method)
+        sim.prepare_matrices()
+        if u0 is None:
+            u0 = synthetic_state(sim.shape())
+        sim.ctx.upload(U_PREV, u0)
+        sim.ctx.compute_rhs(sim.substeps()[0].form, U_PREV, U)
+        outs.append(sim.ctx.download(U))
+    assert rel_l2(outs[1], outs[0]) < 1e-14
+
+
 def test_heat3d_100_steps_vs_reference_golden(golden):
     """BASELINE.json configs[0]: heat_3d p=2, 12^3, dt=1e-7, 100 steps from the shipped initial state."""
     g = golden["problems"]

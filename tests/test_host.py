@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     assert declared == set(_lib.EXPORTS)
-    assert _lib.load().adsb_abi_version() == 1
+    assert _lib.load().adsb_abi_version() == 2
 
 
 def test_gauss_tables_knots_matrices_factors_vs_golden(golden):
