@@ -212,7 +212,7 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     }();
     if (use_tile) {
         StageTimer t(c, 1 + axis);
-        const int rc = launch_sweep_tile(F, G, contig, c->stream);
+        const int rc = launch_sweep_tile(F, G, contig, off_in_h, off_out_h, c->stream);
         if (rc == 0) {
             c->launches++;
             return ADSB_OK;

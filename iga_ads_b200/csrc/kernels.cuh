@@ -8,7 +8,8 @@ namespace adsb {
 
 constexpr int SWEEP_CH = 18;  // columns per chunk (one chunk per thread, held in registers)
 constexpr int SWEEP_RL = 2;   // lines per thread: they share every coefficient load and interleave for ILP
-constexpr int SWEEP_MAX_DEPTH_DEV = 6;  // == SWEEP_MAX_DEPTH of internal.hpp
+constexpr int SWEEP_MAX_DEPTH_DEV = 6;
+constexpr int SWEEP_MAX_BOXES = 16;      // TMA boxes per tile and direction (tile-streaming sweep kernel)  // == SWEEP_MAX_DEPTH of internal.hpp
 
 // One factorised band matrix, prepared by build_sweep_plan (host_setup.cpp).
 struct SweepFactor {
@@ -47,12 +48,20 @@ struct SweepTileGeom {
     int L0, L1;        // lines: l0 in [0, L0) (x for the strided sweeps), l1 in [0, L1)
     int nb0, ntiles;   // tiles of 16 lines along l0; nb0 * L1 tiles in all
     int pitch;         // CONTIG: shared row pitch of a line (doubles)
-    int BR, NBX;       // STRIDED: TMA box rows, boxes per tile
+    // STRIDED: a tile is moved as boxes of whole rows, one tensor map per box (exact extents, so a
+    // box never spills over its neighbour): maps[0 .. nbox_in) load, maps[nbox_in .. +nbox_out) store
+    const void* maps;  // CUtensorMap array in global memory
+    int nbox_in, nbox_out;
+    int row0_in[SWEEP_MAX_BOXES], row0_out[SWEEP_MAX_BOXES];  // first tile row of each box
+    int load_bytes;    // sum of the load boxes (mbarrier transaction count)
     int tile_doubles;  // shared-memory doubles per ring slot
     int nbuf;          // ring depth
 };
-// 0: launched; -1: not eligible (caller falls back to launch_sweep); otherwise a cudaError_t
-int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cudaStream_t st);
+// 0: launched; -1: not eligible (caller falls back to launch_sweep); otherwise a cudaError_t.
+// off_in_h / off_out_h: optional host row-offset tables (see adsb_sweep_view); they must be piecewise
+// linear with few pieces (the block layouts of an all-to-all are).
+int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
+                      const long long* off_out_h, cudaStream_t st);
 
 // returns cudaError_t as int
 int launch_sweep(const SweepFactor& F, const SweepGeom& G, bool contig, int NLt, cudaStream_t st);

@@ -75,11 +75,12 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepFactor F, cons
             }
             mbar_wait(&bar, 0);
         } else {
-            for (int ln = 0; ln < lines; ++ln) {
-                const double* row = src + ln * G.s0_in;
-                double* dst = tile + ln * G.pitch;
-#pragma unroll 4
-                for (int j = tid; j < n; j += nthr) dst[j] = __ldcs(row + j);
+            // one flat loop over (line, column): every thread has many independent loads in flight
+            const int total = lines * n;
+#pragma unroll 8
+            for (int idx = tid; idx < total; idx += nthr) {
+                const int ln = idx / n, j = idx - ln * n;
+                tile[ln * G.pitch + j] = __ldcs(src + ln * G.s0_in + j);
             }
             __syncthreads();
         }
@@ -160,11 +161,11 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepFactor F, cons
             }
         } else {
             __syncthreads();
-            for (int ln = 0; ln < lines; ++ln) {
-                double* row = dstb + ln * G.s0_out;
-                const double* srow = tile + ln * G.pitch;
-#pragma unroll 4
-                for (int j = tid; j < n; j += nthr) __stcs(row + j, srow[j]);
+            const int total = lines * n;
+#pragma unroll 8
+            for (int idx = tid; idx < total; idx += nthr) {
+                const int ln = idx / n, j = idx - ln * n;
+                __stcs(dstb + ln * G.s0_out + j, tile[ln * G.pitch + j]);
             }
         }
     } else {

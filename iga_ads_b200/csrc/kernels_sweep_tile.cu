@@ -13,8 +13,12 @@
 // the bytes in flight.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "kernels.cuh"
 #include "sweep_core.cuh"
@@ -44,8 +48,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Block = ncons consumer threads (NLt lanes x chunks, padded to whole warps) + one producer warp.
 template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
 __global__ void __launch_bounds__(288, 1)
-    sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G, const __grid_constant__ CUtensorMap tm_in,
-                      const __grid_constant__ CUtensorMap tm_out) {
+    sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G) {
     constexpr int RL = SWEEP_RL, NLt = NL / RL;
     constexpr int LF = KL + (KL & 1), LB = (KD + 1) + ((KD + 1) & 1), LC = (KD + KL) + ((KD + KL) & 1);
     constexpr int MD = SWEEP_MAX_DEPTH_DEV;
@@ -105,8 +108,9 @@ __global__ void __launch_bounds__(288, 1)
                 for (int ln = 0; ln < lines; ++ln)
                     bulk_g2s(dst + ln * G.pitch, src + ln * G.s0_in, (uint32_t) (n * 8), &full[b]);
             } else {
-                mbar_expect_tx(&full[b], (uint32_t) (G.NBX * G.BR * NL * 8));
-                for (int k = 0; k < G.NBX; ++k) tma_load_3d(dst + k * G.BR * NL, &tm_in, bx * NL, k * G.BR, m, &full[b]);
+                const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(G.maps);
+                mbar_expect_tx(&full[b], (uint32_t) G.load_bytes);
+                for (int k = 0; k < G.nbox_in; ++k) tma_load_3d(dst + G.row0_in[k] * NL, maps + k, bx * NL, 0, m, &full[b]);
             }
         };
         auto issue_store = [&](int i) {
@@ -119,7 +123,8 @@ __global__ void __launch_bounds__(288, 1)
                 double* dst = G.out + (long long) (bx * NL) * G.s0_out + (long long) m * G.s1_out;
                 for (int ln = 0; ln < lines; ++ln) bulk_s2g(dst + ln * G.s0_out, src + ln * G.pitch, (uint32_t) (n * 8));
             } else {
-                for (int k = 0; k < G.NBX; ++k) tma_store_3d(&tm_out, bx * NL, k * G.BR, m, src + k * G.BR * NL);
+                const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(G.maps) + G.nbox_in;
+                for (int k = 0; k < G.nbox_out; ++k) tma_store_3d(maps + k, bx * NL, 0, m, src + G.row0_out[k] * NL);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         };
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(288, 1)
     }
 }
 
-using tile_kern_t = void (*)(const SweepFactor, const SweepTileGeom, const CUtensorMap, const CUtensorMap);
+using tile_kern_t = void (*)(const SweepFactor, const SweepTileGeom);
 
 template <int P, bool PIV, int NL>
 tile_kern_t pick_mode(bool contig) {
@@ -245,31 +250,65 @@ encode_fn_t encode_fn() {
     return fn;
 }
 
-// 3-D map over (x, sweep axis, other axis) with element strides (1, sj, s1); box NL x BR x 1
-bool make_map(CUtensorMap* m, const double* base, int L0, int n, int L1, long long sj, long long s1, int BR, int NL) {
+// 3-D map over (x, rows of one box, other axis) with element strides (1, sj, s1); box NL x rows x 1
+bool make_map(CUtensorMap* m, const double* base, int L0, int rows, int L1, long long sj, long long s1, int NL) {
     encode_fn_t enc = encode_fn();
     if (!enc) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t) L0, (cuuint64_t) n, (cuuint64_t) (L1 > 0 ? L1 : 1)};
-    const cuuint64_t strides[2] = {(cuuint64_t) sj * 8, (cuuint64_t) (L1 > 1 ? s1 : sj * n) * 8};
-    const cuuint32_t box[3] = {(cuuint32_t) NL, (cuuint32_t) BR, 1};
+    if (sj <= 0) sj = 2;  // single row: any valid stride
+    const cuuint64_t dims[3] = {(cuuint64_t) L0, (cuuint64_t) rows, (cuuint64_t) (L1 > 0 ? L1 : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t) sj * 8, (cuuint64_t) (L1 > 1 ? s1 : sj * rows) * 8};
+    const cuuint32_t box[3] = {(cuuint32_t) NL, (cuuint32_t) rows, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*) base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
            CUDA_SUCCESS;
 }
 
+struct Box {
+    int row0, rows;
+    long long off, stride;  // element offset of its first row, row stride
+};
+
+// Cut rows 0..n-1 (offset off[j], or j*sj) into boxes of <= 256 rows with constant stride.
+bool cut_boxes(int n, const long long* off, long long sj, std::vector<Box>& out) {
+    out.clear();
+    int j = 0;
+    while (j < n) {
+        int e = j + 1;
+        long long stride = sj;
+        if (off) {
+            stride = e < n ? off[e] - off[j] : 0;
+            while (e < n && off[e] - off[e - 1] == stride) ++e;
+        } else {
+            e = n;
+        }
+        // [j, e) is linear; split evenly into pieces of at most 256 rows
+        const int len = e - j, pieces = (len + 255) / 256, per = (len + pieces - 1) / pieces;
+        for (int r = j; r < e; r += per) {
+            Box b{r, std::min(per, e - r), off ? off[r] : (long long) r * sj, stride};
+            out.push_back(b);
+        }
+        j = e;
+    }
+    return (int) out.size() <= SWEEP_MAX_BOXES;
+}
+
+std::mutex g_map_mutex;
+std::map<std::vector<long long>, void*> g_map_cache;  // encoded maps already resident on the device
+
 }  // namespace
 
 // Returns cudaSuccess (0) when the tile kernel was launched, -1 when this sweep is not eligible (the
 // caller then uses the register-path kernel), or a CUDA error.
-int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cudaStream_t st) {
+int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
+                      const long long* off_out_h, cudaStream_t st) {
     static const int NL = [] {
         const char* e = getenv("ADSB_SWEEP_NL");
         const int v = e ? atoi(e) : 16;
         return v == 12 ? 12 : 16;
     }();
     const int NLt = NL / SWEEP_RL;
-    if (G.off_in || G.off_out) return -1;
+    if (contig && (off_in_h || off_out_h)) return -1;
     const int ncons = (NLt * F.SC + 31) / 32 * 32;
     if (ncons > 256) return -1;
     if (contig && (SWEEP_CH % 2 || F.KL % 2)) return -1;  // the 128-bit chunk path needs even CH and KL
@@ -287,7 +326,6 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cud
     T.nb0 = (G.L0 + NL - 1) / NL;
     T.ntiles = T.nb0 * G.L1;
     const int rows_needed = F.SC * SWEEP_CH + F.KL;
-    CUtensorMap tm_in{}, tm_out{};
     if (contig) {
         if (!ptr_ok || !even(F.n) || !even(G.s0_in) || !even(G.s1_in) || !even(G.s0_out) || !even(G.s1_out)) return -1;
         int pitch = rows_needed + (rows_needed & 1);
@@ -295,15 +333,46 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cud
         T.pitch = pitch;
         T.tile_doubles = NL * pitch;
     } else {
-        if (!ptr_ok || G.s0_in != 1 || G.s0_out != 1 || !even(G.sj_in) || !even(G.sj_out) ||
-            (G.L1 > 1 && (!even(G.s1_in) || !even(G.s1_out))))
-            return -1;
-        T.NBX = (F.n + 255) / 256;
-        T.BR = (F.n + T.NBX - 1) / T.NBX;
-        const int rows = T.NBX * T.BR > rows_needed ? T.NBX * T.BR : rows_needed;
-        T.tile_doubles = rows * NL;
-        if (!make_map(&tm_in, G.in, G.L0, F.n, G.L1, G.sj_in, G.s1_in, T.BR, NL)) return -1;
-        if (!make_map(&tm_out, G.out, G.L0, F.n, G.L1, G.sj_out, G.s1_out, T.BR, NL)) return -1;
+        if (!ptr_ok || G.s0_in != 1 || G.s0_out != 1 || (G.L1 > 1 && (!even(G.s1_in) || !even(G.s1_out)))) return -1;
+        std::vector<Box> bin, bout;
+        if (!cut_boxes(F.n, off_in_h, G.sj_in, bin) || !cut_boxes(F.n, off_out_h, G.sj_out, bout)) return -1;
+        for (const auto& b : bin)
+            if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+        for (const auto& b : bout)
+            if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+        T.tile_doubles = rows_needed * NL;
+        T.nbox_in = (int) bin.size();
+        T.nbox_out = (int) bout.size();
+        T.load_bytes = 0;
+        std::vector<long long> key = {(long long) (uintptr_t) G.in, (long long) (uintptr_t) G.out, G.L0, G.L1, F.n, NL,
+                                      G.s1_in, G.s1_out};
+        for (size_t k = 0; k < bin.size(); ++k) {
+            T.row0_in[k] = bin[k].row0;
+            T.load_bytes += bin[k].rows * NL * 8;
+            key.insert(key.end(), {bin[k].row0, bin[k].rows, bin[k].off, bin[k].stride});
+        }
+        for (size_t k = 0; k < bout.size(); ++k) {
+            T.row0_out[k] = bout[k].row0;
+            key.insert(key.end(), {-1 - bout[k].row0, bout[k].rows, bout[k].off, bout[k].stride});
+        }
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it == g_map_cache.end()) {
+            std::vector<CUtensorMap> maps(bin.size() + bout.size());
+            for (size_t k = 0; k < bin.size(); ++k)
+                if (!make_map(&maps[k], G.in + bin[k].off, G.L0, bin[k].rows, G.L1, bin[k].stride, G.s1_in, NL)) return -1;
+            for (size_t k = 0; k < bout.size(); ++k)
+                if (!make_map(&maps[bin.size() + k], G.out + bout[k].off, G.L0, bout[k].rows, G.L1, bout[k].stride, G.s1_out,
+                              NL))
+                    return -1;
+            void* d = nullptr;
+            if (cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return -1;
+            cudaError_t e = cudaMemcpyAsync(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `maps` is a local
+            if (e != cudaSuccess) return (int) e;
+            it = g_map_cache.emplace(std::move(key), d).first;
+        }
+        T.maps = it->second;
     }
     T.tile_doubles = (T.tile_doubles + 15) & ~15;  // 128 B granules
     const int LF = F.KL + (F.KL & 1), LB = (F.KD + 1) + ((F.KD + 1) & 1), LC = (F.KD + F.KL) + ((F.KD + F.KL) & 1);
@@ -329,7 +398,7 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, cud
     }();
     dim3 block(ncons + 32, 1, 1);
     dim3 grid(T.ntiles < sms ? T.ntiles : sms, 1, 1);
-    k<<<grid, block, smem, st>>>(F, T, tm_in, tm_out);
+    k<<<grid, block, smem, st>>>(F, T);
     return (int) cudaGetLastError();
 }
 
