@@ -350,9 +350,10 @@ int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view&
     g.alpha = f.alpha;
     g.gamma = f.gamma;
     StageTimer t(c, 0);
-    cudaError_t e = (cudaError_t) launch_rhs_collapsed(c->ndim, ops, g, c->stream);
+    int nl = 1;
+    cudaError_t e = (cudaError_t) launch_rhs_collapsed(c->ndim, ops, g, c->stream, &nl);
     if (e != cudaSuccess) return cuda_fail(e, "rhs kernel launch");
-    c->launches++;
+    c->launches += nl;
     return ADSB_OK;
 }
 

@@ -88,7 +88,14 @@ struct RhsGeom {
     int out_lo[3], out_n[3];  // box to produce
     double alpha, beta[3], gamma;
 };
-int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStream_t st);
+// *nlaunch (optional) receives the number of kernels launched
+int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStream_t st, int* nlaunch = nullptr);
+// TMA-fed 3-D variant (kernels_rhs_tma.cu).  0: launched; -1: not eligible; otherwise a cudaError_t.
+int launch_rhs_tma(const RhsOps& ops, const RhsGeom& G, cudaStream_t st);
+// Encode a 3-D FP64 tiled tensor map (element strides of dims 1 and 2; dim 0 is contiguous) into *map
+// (a CUtensorMap, 128 bytes, 64 B aligned).  False when the driver entry point is missing or refuses.
+bool encode_tensor_map3(void* map, const double* base, const unsigned long long dims[3],
+                        const unsigned long long strides[2], const unsigned box[3]);
 
 // Per-axis quadrature tables on the device (layout of adsb_basis_tables, ders = 1).
 struct QuadAxes {

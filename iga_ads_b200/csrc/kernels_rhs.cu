@@ -378,60 +378,80 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) rhs_collapsed_kernel(const R
 }
 
 // Direct evaluation of the same operator for a narrow box of outputs (the x remainder of the tiling):
-// one thread per DOF, products in the same x -> y -> z order.  Tiny share of the work.
+// one thread per (x, y) column and z segment, products in the same x -> y -> z order; the thread marches
+// along z with the 2P+1 partial output planes in registers, so every input plane is read once per
+// segment (+2P halo planes) instead of 2P+1 times.  Tiny share of the work.
+constexpr int EDGE_ZSEG = 16;
 template <int P, bool D3>
 __global__ void rhs_edge_kernel(const RhsOps ops, const RhsGeom g) {
     constexpr int W = 2 * P + 1, WP = W + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int bw = g.out_n[0];
-    const int xi = idx % bw, yi = idx / bw, zi = blockIdx.y;
+    const int xi = idx % bw, yi = idx / bw;
     if (yi >= g.out_n[1]) return;
     const int nx = ops.n[0], ny = ops.n[1], nz = D3 ? ops.n[2] : 1;
-    const int gx = g.out_lo[0] + xi, gy = g.out_lo[1] + yi, gz = D3 ? g.out_lo[2] + zi : 0;
+    const int gx = g.out_lo[0] + xi, gy = g.out_lo[1] + yi;
     const int rx0 = max(0, g.in_lo[0]), rx1 = min(nx, g.in_lo[0] + g.in_n[0]);
     const int ry0 = max(0, g.in_lo[1]), ry1 = min(ny, g.in_lo[1] + g.in_n[1]);
     const int rz0 = D3 ? max(0, g.in_lo[2]) : 0, rz1 = D3 ? min(nz, g.in_lo[2] + g.in_n[2]) : 1;
-    double kx[W], mx[W];
+    const int zs = D3 ? g.out_lo[2] + blockIdx.y * EDGE_ZSEG : 0;
+    const int ze = D3 ? min(zs + EDGE_ZSEG, g.out_lo[2] + g.out_n[2]) : 1;
+    double kx[W], mx[W], my[W], sy[W];
 #pragma unroll
     for (int m = 0; m < W; ++m) {
         const double a = ops.Mx[gx * W + m], s = ops.Sx[gx * W + m];
         mx[m] = a;
         kx[m] = g.alpha * a - g.beta[0] * s;
+        my[m] = ops.My[gy * W + m];
+        sy[m] = -g.beta[1] * ops.Sy[gy * W + m];
     }
-    double acc = 0.0;
-    for (int dz = (D3 ? -P : 0); dz <= (D3 ? P : 0); ++dz) {
-        const int k = gz + dz;
-        if (k < rz0 || k >= rz1) continue;
-        double G = 0.0, H = 0.0;
-        for (int dy = -P; dy <= P; ++dy) {
-            const int yy = gy + dy;
-            if (yy < ry0 || yy >= ry1) continue;
-            const double* row = g.in + (long long) (yy - g.in_lo[1]) * g.si[1] +
-                                (D3 ? (long long) (k - g.in_lo[2]) * g.si[2] : 0) - g.in_lo[0];
-            double a = 0.0, b = 0.0;
+    double acc[W];  // acc[d]: partial sum of output plane k - P + d while input plane k is scattered
 #pragma unroll
-            for (int m = 0; m < W; ++m) {
-                const int xx = gx - P + m;
-                const double uv = (xx >= rx0 && xx < rx1) ? __ldg(row + xx) : 0.0;
-                a = fma(kx[m], uv, a);
-                b = fma(mx[m], uv, b);
+    for (int d = 0; d < W; ++d) acc[d] = 0.0;
+    long long o = (long long) xi + (long long) yi * g.so[1] + (D3 ? (long long) (zs - g.out_lo[2]) * g.so[2] : 0);
+    for (int k = (D3 ? zs - P : 0); k < (D3 ? ze + P : 1); ++k) {
+        double G = 0.0, H = 0.0;
+        if (k >= rz0 && k < rz1) {
+#pragma unroll
+            for (int dy = -P; dy <= P; ++dy) {
+                const int yy = gy + dy;
+                if (yy < ry0 || yy >= ry1) continue;
+                const double* row = g.in + (long long) (yy - g.in_lo[1]) * g.si[1] +
+                                    (D3 ? (long long) (k - g.in_lo[2]) * g.si[2] : 0) - g.in_lo[0];
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int m = 0; m < W; ++m) {
+                    const int xx = gx - P + m;
+                    const double uv = (xx >= rx0 && xx < rx1) ? __ldg(row + xx) : 0.0;
+                    a = fma(kx[m], uv, a);
+                    b = fma(mx[m], uv, b);
+                }
+                G = fma(my[dy + P], a, G);
+                G = fma(sy[dy + P], b, G);
+                H = fma(my[dy + P], b, H);
             }
-            const double myv = ops.My[gy * W + dy + P], syv = -g.beta[1] * ops.Sy[gy * W + dy + P];
-            G = fma(myv, a, G);
-            G = fma(syv, b, G);
-            H = fma(myv, b, H);
         }
-        if (D3) {
-            const double* zc = ops.MSzT + (long long) (k + P) * 2 * WP + (gz - k + P);  // A(gz, k)
-            acc = fma(zc[0], G, acc);
-            acc = fma(zc[WP], -g.beta[2] * H, acc);
+        if (!D3) {
+            acc[0] = G;
         } else {
-            acc = G;
+            const double* zc = ops.MSzT + (long long) (k + P) * 2 * WP;  // column k: A(k-P .. k+P, k)
+            const double Hs = -g.beta[2] * H;
+#pragma unroll
+            for (int d = 0; d < W; ++d) {
+                acc[d] = fma(zc[d], G, acc[d]);
+                acc[d] = fma(zc[WP + d], Hs, acc[d]);
+            }
         }
+        if (!D3 || k - P >= zs) {  // output plane k - P is complete
+            double v = acc[0];
+            if (g.forcing) v = fma(g.gamma, g.forcing[o], v);
+            g.out[o] = v;
+            o += D3 ? g.so[2] : 0;
+        }
+#pragma unroll
+        for (int d = 0; d + 1 < W; ++d) acc[d] = acc[d + 1];
+        acc[W - 1] = 0.0;
     }
-    const long long o = (long long) xi + (long long) yi * g.so[1] + (D3 ? (long long) zi * g.so[2] : 0);
-    if (g.forcing) acc = fma(g.gamma, g.forcing[o], acc);
-    g.out[o] = acc;
 }
 
 int sm_count() {
@@ -445,7 +465,7 @@ int sm_count() {
 }
 
 template <int P, int NPT, int NWARP, int MINB, bool YREG>
-int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st) {
+int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bool try_tma, int* nlaunch) {
     using T = RhsTile<P, NPT, NWARP>;
     if (g0.si[0] != 1 || g0.so[0] != 1) return (int) cudaErrorInvalidValue;  // x must be contiguous
     // x remainder of the 64-wide tiling: a nearly empty tile column would cost a full one, so a
@@ -490,13 +510,17 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st) {
         kern<<<grid, block, smem, st>>>(ops, g, zseg);
         return (int) cudaGetLastError();
     };
-    int rc;
-    if (ndim == 3)
+    int rc = -1;
+    if (ndim == 3 && try_tma) rc = launch_rhs_tma(ops, g, st);  // -1: not eligible
+    if (rc != -1)
+        ;
+    else if (ndim == 3)
         rc = vec ? go(rhs_collapsed_kernel<P, NPT, NWARP, MINB, YREG, true, true>)
                  : go(rhs_collapsed_kernel<P, NPT, NWARP, MINB, YREG, true, false>);
     else
         rc = vec ? go(rhs_collapsed_kernel<P, NPT, NWARP, MINB, YREG, false, true>)
                  : go(rhs_collapsed_kernel<P, NPT, NWARP, MINB, YREG, false, false>);
+    if (nlaunch) *nlaunch = split ? 2 : 1;
     if (rc != (int) cudaSuccess || !split) return rc;
     RhsGeom e = g0;
     e.out_lo[0] = g0.out_lo[0] + g.out_n[0];
@@ -504,7 +528,7 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st) {
     e.out = g0.out + g.out_n[0];
     if (g0.forcing) e.forcing = g0.forcing + g.out_n[0];
     const long long cols = (long long) rem * e.out_n[1];
-    dim3 eb(128, 1, 1), eg((unsigned) ((cols + 127) / 128), ndim == 3 ? e.out_n[2] : 1, 1);
+    dim3 eb(128, 1, 1), eg((unsigned) ((cols + 127) / 128), ndim == 3 ? (e.out_n[2] + EDGE_ZSEG - 1) / EDGE_ZSEG : 1, 1);
     if (ndim == 3)
         rhs_edge_kernel<P, true><<<eg, eb, 0, st>>>(ops, e);
     else
@@ -520,24 +544,27 @@ __global__ void set_plane_kernel(double* t, long long sa, long long sb, int na, 
 
 }  // namespace
 
-int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
+int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& g, cudaStream_t st, int* nlaunch) {
     const int p = ops.p[0];
     if (ops.p[1] != p || (ndim == 3 && ops.p[2] != p)) return (int) cudaErrorInvalidValue;
+    // ADSB_RHS_VARIANT: 0 = TMA-fed kernel where eligible (kernels_rhs_tma.cu), else the cp.async kernel;
+    // 10 = cp.async kernel only; 11 / 12 = its other launch shapes (kept for measurements)
     static const int variant = [] {
         const char* e = getenv("ADSB_RHS_VARIANT");
         return e ? atoi(e) : 0;
     }();
+    const bool tma = variant < 10;
     switch (p) {
-    case 1: return launch_p<1, 2, 8, 2, false>(ndim, ops, g, st);
+    case 1: return launch_p<1, 2, 8, 2, false>(ndim, ops, g, st, tma, nlaunch);
     case 2:
-        // measured at 514^3 on B200: 0.93 ms (8 warps, 1 CTA/SM, y rows in registers), 1.02 (variant 1:
-        // 2 CTAs/SM, y rows broadcast from shared), 1.11 (variant 2: 12 warps)
-        if (variant == 1) return launch_p<2, 2, 8, 2, false>(ndim, ops, g, st);
-        if (variant == 2) return launch_p<2, 2, 12, 1, true>(ndim, ops, g, st);
-        return launch_p<2, 2, 8, 1, true>(ndim, ops, g, st);
-    case 3: return launch_p<3, 1, 8, 2, false>(ndim, ops, g, st);
-    case 4: return launch_p<4, 1, 8, 1, false>(ndim, ops, g, st);
-    case 5: return launch_p<5, 1, 8, 1, false>(ndim, ops, g, st);
+        // cp.async kernel, measured at 514^3 on B200: 0.93 ms (8 warps, 1 CTA/SM, y rows in registers), 1.02
+        // (variant 11: 2 CTAs/SM, y rows broadcast from shared), 1.11 (variant 12: 12 warps)
+        if (variant == 11) return launch_p<2, 2, 8, 2, false>(ndim, ops, g, st, false, nlaunch);
+        if (variant == 12) return launch_p<2, 2, 12, 1, true>(ndim, ops, g, st, false, nlaunch);
+        return launch_p<2, 2, 8, 1, true>(ndim, ops, g, st, tma, nlaunch);
+    case 3: return launch_p<3, 1, 8, 2, false>(ndim, ops, g, st, tma, nlaunch);
+    case 4: return launch_p<4, 1, 8, 1, false>(ndim, ops, g, st, tma, nlaunch);
+    case 5: return launch_p<5, 1, 8, 1, false>(ndim, ops, g, st, tma, nlaunch);
     default: return (int) cudaErrorInvalidValue;
     }
 }

@@ -1,0 +1,397 @@
+// kernels_rhs_tma.cu -- K1 (collapsed form), TMA-fed 3-D variant, FP64, sm_100a.
+//
+// Same operator and the same x -> y -> z product order as kernels_rhs.cu (see there for the algebra;
+// replaces examples/heat/heat_3d.hpp:49-67, implicit/implicit.hpp:132-182, scalability/test3d.hpp:66-95).
+// kernels_rhs.cu is bound by the shared-memory pipe (1.16 LSU wavefronts per DOF, profiles/r1b_*):
+// every plane goes global -> shared (LDGSTS) -> x product -> shared -> y product with a (NPT+2p)/NPT
+// re-read.  This kernel moves fewer bytes through that pipe:
+//   * raw planes (tile + halo) are fetched by the TMA engine: one cp.async.bulk.tensor per plane and CTA
+//     (SASS UTMALDG), issued by one thread, completion on an mbarrier; the halo outside the array is
+//     zero-filled by the engine -- no per-thread address arithmetic, predicates or LSU wavefronts;
+//   * a warp does the x product of exactly the NPT rows it owns in the y product and keeps those
+//     P/Q values in registers; only the 2p neighbouring rows come back out of shared memory
+//     (y re-read 2p/NPT instead of (NPT+2p)/NPT), the 2p halo rows of the tile are shared out one per warp;
+//   * y and z coefficient rows are broadcast reads of small shared tables (z table staged once per
+//     CTA instead of a global load per plane);
+//   * small CTAs (NWARP warps, several per SM) so that the shared-memory-heavy x phase of one CTA
+//     overlaps the FP64-heavy y/z phase of another.
+// z product as in kernels_rhs.cu: scatter onto 2p+1 partial output planes held in registers, plane
+// loop unrolled 2p+1 times so the window rotation is register renaming.  One __syncthreads per plane.
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "tma.cuh"
+
+namespace adsb {
+
+namespace {
+
+constexpr int TXV = 64;  // tile width in DOFs: 32 lanes x 2
+
+template <int P, int NPT, int NWARP, int NSTAGE>
+struct Cfg {
+    static constexpr int W = 2 * P + 1;
+    static constexpr int PH = P + (P & 1);   // x halo rounded up to even: 16 B aligned windows
+    static constexpr int TY = NWARP * NPT;   // output rows per tile
+    static constexpr int UH = TY + 2 * P;    // rows of the raw / P / Q tiles
+    static constexpr int RW = TXV + 2 * PH;  // raw row length in doubles
+    static constexpr int NTH = NWARP * 32;
+    static constexpr int RAW_BYTES = UH * RW * 8;                       // one TMA box
+    static constexpr int RAW_STRIDE = (RAW_BYTES + 127) / 128 * 128;    // stage pitch (TMA destination: 128 B aligned)
+    static constexpr int PQ_BYTES = UH * TXV * 8;                       // one P (or Q) tile
+    static constexpr int YC_BYTES = TY * W * 16;                        // [TY][W] (My, -beta_y Sy)
+    static constexpr int FIXED_BYTES = NSTAGE * RAW_STRIDE + 4 * PQ_BYTES + YC_BYTES + NSTAGE * 8 + 8 + 128;
+    static constexpr int NHALO = (2 * P + NWARP - 1) / NWARP;           // halo rows a warp may have to do
+};
+
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts2(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_box3(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+template <int P, int NPT, int NWARP, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB)
+    rhs_tma_kernel(const __grid_constant__ CUtensorMap tmap, const RhsOps ops, const RhsGeom g, int zseg) {
+    using C = Cfg<P, NPT, NWARP, NSTAGE>;
+    constexpr int W = C::W, PH = C::PH, TY = C::TY, UH = C::UH, RW = C::RW, NTH = C::NTH;
+    constexpr uint32_t RAWS = C::RAW_STRIDE, PQB = C::PQ_BYTES;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base_u = (smem_addr(smem_raw) + 127u) & ~127u;
+    unsigned char* base_p = smem_raw + (base_u - smem_addr(smem_raw));
+    const uint32_t raw_u = base_u;                     // [NSTAGE][UH][RW]
+    const uint32_t pq_u = raw_u + NSTAGE * RAWS;       // [2 buffers][P | Q][UH][TXV]
+    const uint32_t yc_u = pq_u + 4 * PQB;              // [TY][W] double2
+    const uint32_t bar_u = yc_u + C::YC_BYTES;         // NSTAGE mbarriers
+    const uint32_t zt_u = bar_u + NSTAGE * 8 + ((NSTAGE & 1) ? 8 : 0);  // [NP][W] double2 (Mz, -beta_z Sz) columns
+    double2* yc = reinterpret_cast<double2*>(base_p + (yc_u - base_u));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_p + (bar_u - base_u));
+    double2* zt = reinterpret_cast<double2*>(base_p + (zt_u - base_u));
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int x0 = g.out_lo[0] + blockIdx.x * TXV;
+    const int y0 = g.out_lo[1] + blockIdx.y * TY;
+    const int nx = ops.n[0], ny = ops.n[1];
+    const int zs = g.out_lo[2] + blockIdx.z * zseg;
+    const int ze = min(zs + zseg, g.out_lo[2] + g.out_n[2]);
+    const int kb = zs - P;
+    const int NP = ze - zs + 2 * P;  // input planes kb .. kb + NP - 1
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // y rows of the tile and z columns of the planes this CTA marches through
+    for (int i = tid; i < TY * W; i += NTH) {
+        const int r = i / W, m = i - r * W;
+        const int gyc = min(y0 + r, ny - 1);
+        yc[i] = make_double2(ops.My[gyc * W + m], -g.beta[1] * ops.Sy[gyc * W + m]);
+    }
+    {
+        // the z column table carries P zero rows on both sides, so planes outside the domain need no clamp
+        const double* zr = ops.MSzT + (long long) (kb + P) * 2 * (W + 1);
+        for (int i = tid; i < NP * W; i += NTH) {
+            const int q = i / W, d = i - q * W;
+            zt[i] = make_double2(zr[q * 2 * (W + 1) + d], -g.beta[2] * zr[q * 2 * (W + 1) + (W + 1) + d]);
+        }
+    }
+    // coefficient rows of this lane's two x (clamped: out-of-box lanes compute values nobody stores)
+    double kx[2][W], mx[2][W];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int gxc = min(x0 + 2 * lane + b, nx - 1);
+#pragma unroll
+        for (int m = 0; m < W; ++m) {
+            const double a = ops.Mx[gxc * W + m], s = ops.Sx[gxc * W + m];
+            mx[b][m] = a;
+            kx[b][m] = g.alpha * a - g.beta[0] * s;
+        }
+    }
+    __syncthreads();
+
+    // TMA box of plane k: coordinates relative to the box `in` covers; everything outside is zero-filled
+    const int c0 = x0 - PH - g.in_lo[0], c1 = y0 - P - g.in_lo[1], c2b = kb - g.in_lo[2];
+    auto issue = [&](int q, int stage) {
+        mbar_expect_tx_u32(bar_u + stage * 8, C::RAW_BYTES);
+        tma_load_box3(raw_u + stage * RAWS, &tmap, c0, c1, c2b + q, bar_u + stage * 8);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s)
+            if (s < NP) issue(s, s);
+    }
+
+    // x product of raw row j: 2*PH+2 inputs -> P, Q for the lane's two x
+    auto xrow = [&](uint32_t src, double (&a)[2], double (&b)[2]) {
+        double win[2 * PH + 2];
+#pragma unroll
+        for (int i = 0; i < 2 * PH + 2; i += 2) {
+            const double2 t = lds2(src + i * 8);
+            win[i] = t.x;
+            win[i + 1] = t.y;
+        }
+#pragma unroll
+        for (int xb = 0; xb < 2; ++xb) {
+            a[xb] = kx[xb][0] * win[xb + PH - P];
+            b[xb] = mx[xb][0] * win[xb + PH - P];
+#pragma unroll
+            for (int m = 1; m < W; ++m) {
+                a[xb] = fma(kx[xb][m], win[xb + PH - P + m], a[xb]);
+                b[xb] = fma(mx[xb][m], win[xb + PH - P + m], b[xb]);
+            }
+        }
+    };
+    const uint32_t lane_raw = (uint32_t) (2 * lane) * 8;  // column offset of the lane's window in a raw row
+    const uint32_t lane_pq = (uint32_t) (2 * lane) * 8;   // ... of its pair in a P/Q row
+    const int jown = P + w * NPT;                         // first own row (tile row index, 0 = y0 - P)
+
+    // outputs of this thread: NPT row pairs; offsets inside a plane + marching plane pointers
+    const int gx = x0 + 2 * lane;
+    const int xend = g.out_lo[0] + g.out_n[0];
+    int o_row[NPT];  // -1: nothing to store
+#pragma unroll
+    for (int r = 0; r < NPT; ++r) {
+        const int gy = y0 + w * NPT + r;
+        const bool ok = gy < g.out_lo[1] + g.out_n[1] && gx < xend;
+        o_row[r] = ok ? (int) ((gx - g.out_lo[0]) + (long long) (gy - g.out_lo[1]) * g.so[1]) : -1;
+    }
+    double* o_pl = g.out + (long long) (zs - g.out_lo[2]) * g.so[2];
+    const double* f_pl = g.forcing ? g.forcing + (long long) (zs - g.out_lo[2]) * g.so[2] : nullptr;
+
+    // acc[r][xb][s]: partial sums of output planes; slot (d + rot) % W holds plane q - P + d while
+    // input plane q is being scattered
+    double acc[NPT][2][W];
+#pragma unroll
+    for (int r = 0; r < NPT; ++r)
+#pragma unroll
+        for (int xb = 0; xb < 2; ++xb)
+#pragma unroll
+            for (int s = 0; s < W; ++s) acc[r][xb][s] = 0.0;
+
+    int stage = 0;
+    uint32_t parity = 0, pqbuf = 0;
+    uint32_t zrow_u = zt_u;
+    for (int q0 = 0; q0 < NP; q0 += W) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int q = q0 + j;  // plane q: x, y products and z scatter with rotation j
+            if (q < NP) {
+                mbar_wait_u32(bar_u + stage * 8, parity);
+                const uint32_t raw_s = raw_u + stage * RAWS + lane_raw;
+                const uint32_t pq_s = pq_u + pqbuf * 2 * PQB + lane_pq;
+                // x product: own rows stay in registers; rows a neighbouring warp needs go to shared
+                double pr[NPT][2], qr[NPT][2];
+#pragma unroll
+                for (int r = 0; r < NPT; ++r) {
+                    xrow(raw_s + (uint32_t) ((jown + r) * RW) * 8, pr[r], qr[r]);
+                    if (r < P || r >= NPT - P) {
+                        sts2(pq_s + (uint32_t) ((jown + r) * TXV) * 8, pr[r][0], pr[r][1]);
+                        sts2(pq_s + PQB + (uint32_t) ((jown + r) * TXV) * 8, qr[r][0], qr[r][1]);
+                    }
+                }
+#pragma unroll
+                for (int hh = 0; hh < C::NHALO; ++hh) {
+                    const int h = w + hh * NWARP;  // halo row h of 2P: P rows above the tile, P below
+                    if (h < 2 * P) {
+                        const int jr = h < P ? h : TY + h;
+                        double a[2], b[2];
+                        xrow(raw_s + (uint32_t) (jr * RW) * 8, a, b);
+                        sts2(pq_s + (uint32_t) (jr * TXV) * 8, a[0], a[1]);
+                        sts2(pq_s + PQB + (uint32_t) (jr * TXV) * 8, b[0], b[1]);
+                    }
+                }
+                __syncthreads();
+                // the raw stage is free again: fetch plane q + NSTAGE into it
+                if (tid == 0 && q + NSTAGE < NP) issue(q + NSTAGE, stage);
+
+                // y product: extended column e = 0 .. NPT+2P-1 is tile row w*NPT + e; e in [P, P+NPT) is own
+                double pc[NPT + 2 * P][2], qc[NPT + 2 * P][2];
+#pragma unroll
+                for (int e = 0; e < NPT + 2 * P; ++e) {
+                    if (e >= P && e < P + NPT) {
+                        pc[e][0] = pr[e - P][0]; pc[e][1] = pr[e - P][1];
+                        qc[e][0] = qr[e - P][0]; qc[e][1] = qr[e - P][1];
+                    } else {
+                        const double2 a = lds2(pq_s + (uint32_t) ((w * NPT + e) * TXV) * 8);
+                        const double2 b = lds2(pq_s + PQB + (uint32_t) ((w * NPT + e) * TXV) * 8);
+                        pc[e][0] = a.x; pc[e][1] = a.y;
+                        qc[e][0] = b.x; qc[e][1] = b.y;
+                    }
+                }
+                double G[NPT][2], H[NPT][2];
+#pragma unroll
+                for (int r = 0; r < NPT; ++r) {
+#pragma unroll
+                    for (int m = 0; m < W; ++m) {
+                        const double2 cy = lds2(yc_u + (uint32_t) (((w * NPT + r) * W + m) * 16));
+#pragma unroll
+                        for (int xb = 0; xb < 2; ++xb) {
+                            if (m == 0) {
+                                G[r][xb] = cy.x * pc[r][xb];
+                                H[r][xb] = cy.x * qc[r][xb];
+                            } else {
+                                G[r][xb] = fma(cy.x, pc[r + m][xb], G[r][xb]);
+                                H[r][xb] = fma(cy.x, qc[r + m][xb], H[r][xb]);
+                            }
+                            G[r][xb] = fma(cy.y, qc[r + m][xb], G[r][xb]);
+                        }
+                    }
+                }
+                // z product: scatter plane q onto the 2P+1 output planes it feeds
+#pragma unroll
+                for (int d = 0; d < W; ++d) {
+                    const double2 cz = lds2(zrow_u + d * 16);
+                    const int s = (d + j) % W;
+#pragma unroll
+                    for (int r = 0; r < NPT; ++r)
+#pragma unroll
+                        for (int xb = 0; xb < 2; ++xb) {
+                            acc[r][xb][s] = fma(cz.x, G[r][xb], acc[r][xb][s]);
+                            acc[r][xb][s] = fma(cz.y, H[r][xb], acc[r][xb][s]);
+                        }
+                }
+                zrow_u += W * 16;
+                if (q >= 2 * P) {  // output plane zs + q - 2P is complete
+#pragma unroll
+                    for (int r = 0; r < NPT; ++r) {
+                        if (o_row[r] >= 0) {
+                            double v0 = acc[r][0][j], v1 = acc[r][1][j];
+                            if (f_pl) {
+                                const double2 f = __ldg(reinterpret_cast<const double2*>(f_pl + o_row[r]));
+                                v0 = fma(g.gamma, f.x, v0);
+                                v1 = fma(g.gamma, f.y, v1);
+                            }
+                            __stcs(reinterpret_cast<double2*>(o_pl + o_row[r]), make_double2(v0, v1));
+                        }
+                    }
+                    o_pl += g.so[2];
+                    if (f_pl) f_pl += g.so[2];
+                }
+#pragma unroll
+                for (int r = 0; r < NPT; ++r) {
+                    acc[r][0][j] = 0.0;
+                    acc[r][1][j] = 0.0;
+                }
+                pqbuf ^= 1;
+                if (++stage == NSTAGE) {
+                    stage = 0;
+                    parity ^= 1;
+                }
+            }
+        }
+    }
+}
+
+int sm_count_tma() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+template <int P, int NPT, int NWARP, int NSTAGE, int MINB>
+int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
+    using C = Cfg<P, NPT, NWARP, NSTAGE>;
+    auto kern = rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB>;
+    CUtensorMap map;
+    const unsigned long long dims[3] = {(unsigned long long) g.in_n[0], (unsigned long long) g.in_n[1],
+                                        (unsigned long long) g.in_n[2]};
+    const unsigned long long strides[2] = {(unsigned long long) g.si[1], (unsigned long long) g.si[2]};
+    const unsigned box[3] = {(unsigned) C::RW, (unsigned) C::UH, 1u};
+    if (!encode_tensor_map3(&map, g.in, dims, strides, box)) return -1;
+
+    const int tx = (g.out_n[0] + TXV - 1) / TXV, ty = (g.out_n[1] + C::TY - 1) / C::TY;
+    const int smem_budget = 227 * 1024 / MINB - 1024;
+    const int zcap = (smem_budget - C::FIXED_BYTES) / (C::W * 16) - 2 * P;  // planes whose z columns fit in shared
+    if (zcap < 8 * P) return -1;
+    // z segments: every segment re-reads 2P halo planes and pays a pipeline prologue; choose the count
+    // that minimises (waves of resident CTAs) x (planes per CTA)
+    const long long slots = (long long) sm_count_tma() * MINB;
+    const long long tiles = (long long) tx * ty;
+    long long best = -1;
+    int zseg = 1;
+    for (int ns = 1; ns <= 256 && ns <= g.out_n[2]; ++ns) {
+        const int zs = (g.out_n[2] + ns - 1) / ns;
+        if (zs > zcap) continue;
+        if (ns > 1 && zs < 8 * P) break;
+        const long long waves = (tiles * ((g.out_n[2] + zs - 1) / zs) + slots - 1) / slots;
+        const long long cost = waves * (zs + 2 * P + 4);
+        if (best < 0 || cost < best) {
+            best = cost;
+            zseg = zs;
+        }
+    }
+    if (best < 0) return -1;
+    const int nseg = (g.out_n[2] + zseg - 1) / zseg;
+    const int smem = C::FIXED_BYTES + (zseg + 2 * P) * C::W * 16;
+    cudaError_t e = cudaFuncSetAttribute((const void*) kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int) e;
+    dim3 grid(tx, ty, nseg), block(C::NTH, 1, 1);
+    kern<<<grid, block, smem, st>>>(map, ops, g, zseg);
+    return (int) cudaGetLastError();
+}
+
+}  // namespace
+
+// 0: launched; -1: this problem is not eligible (caller uses the cp.async kernel); else a cudaError_t.
+int launch_rhs_tma(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
+    const int p = ops.p[0];
+    if (ops.p[1] != p || ops.p[2] != p) return -1;
+    auto even = [](long long v) { return (v & 1) == 0; };
+    if (g.si[0] != 1 || g.so[0] != 1) return -1;
+    // TMA: 16 B aligned base and strides; pair stores: even output extents / strides
+    if (!even(g.si[1]) || !even(g.si[2]) || !even(g.so[1]) || !even(g.so[2]) || !even(g.out_n[0])) return -1;
+    if ((uintptr_t) g.in % 16 || (uintptr_t) g.out % 16 || (g.forcing && (uintptr_t) g.forcing % 16)) return -1;
+    for (int d = 0; d < 3; ++d)  // outside `in` reads as zero: only right when `in` does not stick out of the domain
+        if (g.in_lo[d] < 0 || g.in_lo[d] + g.in_n[d] > ops.n[d]) return -1;
+    static const int variant = [] {
+        const char* e = getenv("ADSB_RHS_TMA_VARIANT");
+        return e ? atoi(e) : 0;
+    }();
+    switch (p) {
+    case 2:
+        if (variant == 1) return launch_cfg<2, 4, 4, 4, 2>(ops, g, st);
+        if (variant == 2) return launch_cfg<2, 4, 8, 3, 1>(ops, g, st);
+        if (variant == 3) return launch_cfg<2, 2, 4, 3, 3>(ops, g, st);
+        if (variant == 4) return launch_cfg<2, 2, 8, 3, 2>(ops, g, st);
+        return launch_cfg<2, 4, 4, 3, 2>(ops, g, st);
+    case 3:
+        if (variant == 1) return launch_cfg<3, 2, 6, 3, 2>(ops, g, st);
+        return launch_cfg<3, 2, 6, 3, 1>(ops, g, st);
+    default: return -1;
+    }
+}
+
+}  // namespace adsb

@@ -298,6 +298,19 @@ std::map<std::vector<long long>, void*> g_map_cache;  // encoded maps already re
 
 }  // namespace
 
+bool encode_tensor_map3(void* map, const double* base, const unsigned long long dims[3],
+                        const unsigned long long strides[2], const unsigned box[3]) {
+    encode_fn_t enc = encode_fn();
+    if (!enc) return false;
+    const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t s[2] = {strides[0] * 8, strides[1] * 8};
+    const cuuint32_t b[3] = {box[0], box[1], box[2]};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*) base, d, s, b, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Returns cudaSuccess (0) when the tile kernel was launched, -1 when this sweep is not eligible (the
 // caller then uses the register-path kernel), or a CUDA error.
 int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,

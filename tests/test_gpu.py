@@ -210,7 +210,11 @@ def test_heat3d_100_steps_vs_reference_golden(golden):
 @pytest.mark.parametrize("name,p,ne,dt", [("heat_3d", 2, 62, 1e-7), ("heat_2d", 3, 253, 1e-5),
                                           ("implicit_2d", 3, 200, 1e-2), ("implicit_3d", 3, 30, 1e-2),
                                           ("scalability_3d", 2, 30, 1e-6), ("scalability_3d", 5, 20, 1e-6),
-                                          ("scalability_3d", 4, 21, 1e-6), ("scalability_2d", 3, 130, 1e-6)])
+                                          ("scalability_3d", 4, 21, 1e-6), ("scalability_2d", 3, 130, 1e-6),
+                                          # even extents: the TMA-fed right-hand side; x remainder of the 64-wide
+                                          # tiling through the direct kernel (n = 78, 66) or a partial tile (n = 102)
+                                          ("heat_3d", 2, 76, 1e-7), ("heat_3d", 3, 63, 1e-7), ("heat_3d", 2, 100, 1e-7),
+                                          ("implicit_3d", 3, 31, 1e-2), ("scalability_3d", 3, 29, 1e-6)])
 def test_one_step_vs_oracle(oracle, name, p, ne, dt):
     sim = make_problem(name, p, ne, dt)
     u0 = synthetic_state(sim.shape())
