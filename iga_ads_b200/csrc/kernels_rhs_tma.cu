@@ -78,7 +78,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-template <int P, int NPT, int NWARP, int NSTAGE, int MINB>
+template <int P, int NPT, int NWARP, int NSTAGE, int MINB, bool FORCING>
 __global__ void __launch_bounds__(NWARP * 32, MINB)
     rhs_tma_kernel(const __grid_constant__ CUtensorMap tmap, const RhsOps ops, const RhsGeom g, int zseg) {
     using C = Cfg<P, NPT, NWARP, NSTAGE>;
@@ -150,15 +150,8 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
             if (s < NP) issue(s, s);
     }
 
-    // x product of raw row j: 2*PH+2 inputs -> P, Q for the lane's two x
-    auto xrow = [&](uint32_t src, double (&a)[2], double (&b)[2]) {
-        double win[2 * PH + 2];
-#pragma unroll
-        for (int i = 0; i < 2 * PH + 2; i += 2) {
-            const double2 t = lds2(src + i * 8);
-            win[i] = t.x;
-            win[i + 1] = t.y;
-        }
+    // x product of one loaded window: 2*PH+2 inputs -> P, Q for the lane's two x
+    auto xmul = [&](const double (&win)[2 * PH + 2], double (&a)[2], double (&b)[2]) {
 #pragma unroll
         for (int xb = 0; xb < 2; ++xb) {
             a[xb] = kx[xb][0] * win[xb + PH - P];
@@ -185,7 +178,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
         o_row[r] = ok ? (int) ((gx - g.out_lo[0]) + (long long) (gy - g.out_lo[1]) * g.so[1]) : -1;
     }
     double* o_pl = g.out + (long long) (zs - g.out_lo[2]) * g.so[2];
-    const double* f_pl = g.forcing ? g.forcing + (long long) (zs - g.out_lo[2]) * g.so[2] : nullptr;
+    const double* f_pl = FORCING ? g.forcing + (long long) (zs - g.out_lo[2]) * g.so[2] : nullptr;
 
     // acc[r][xb][s]: partial sums of output planes; slot (d + rot) % W holds plane q - P + d while
     // input plane q is being scattered
@@ -208,64 +201,91 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
                 mbar_wait_u32(bar_u + stage * 8, parity);
                 const uint32_t raw_s = raw_u + stage * RAWS + lane_raw;
                 const uint32_t pq_s = pq_u + pqbuf * 2 * PQB + lane_pq;
-                // x product: own rows stay in registers; rows a neighbouring warp needs go to shared
+                // x product: own rows stay in registers; rows a neighbouring warp needs go to shared.  The
+                // window of the next row is loaded before the current row is multiplied out (the stores
+                // in between would otherwise pin every load behind them).
                 double pr[NPT][2], qr[NPT][2];
+                {
+                    constexpr int NXR = NPT + C::NHALO;  // rows of this thread: own rows, then its halo rows
+                    auto row_of = [&](int i) -> int {    // tile row of the i-th of them
+                        if (i < NPT) return jown + i;
+                        const int h = min(w + (i - NPT) * NWARP, 2 * P - 1);  // surplus warps shadow the last halo row
+                        return h < P ? h : TY + h;
+                    };
+                    double win[2][2 * PH + 2];
+                    auto load_win = [&](int i, double (&wv)[2 * PH + 2]) {
+                        const uint32_t src = raw_s + (uint32_t) (row_of(i) * RW) * 8;
 #pragma unroll
-                for (int r = 0; r < NPT; ++r) {
-                    xrow(raw_s + (uint32_t) ((jown + r) * RW) * 8, pr[r], qr[r]);
-                    if (r < P || r >= NPT - P) {
-                        sts2(pq_s + (uint32_t) ((jown + r) * TXV) * 8, pr[r][0], pr[r][1]);
-                        sts2(pq_s + PQB + (uint32_t) ((jown + r) * TXV) * 8, qr[r][0], qr[r][1]);
-                    }
-                }
+                        for (int c = 0; c < 2 * PH + 2; c += 2) {
+                            const double2 t = lds2(src + c * 8);
+                            wv[c] = t.x;
+                            wv[c + 1] = t.y;
+                        }
+                    };
+                    load_win(0, win[0]);
 #pragma unroll
-                for (int hh = 0; hh < C::NHALO; ++hh) {
-                    const int h = w + hh * NWARP;  // halo row h of 2P: P rows above the tile, P below
-                    if (h < 2 * P) {
-                        const int jr = h < P ? h : TY + h;
+                    for (int i = 0; i < NXR; ++i) {
+                        if (i + 1 < NXR) load_win(i + 1, win[(i + 1) & 1]);
                         double a[2], b[2];
-                        xrow(raw_s + (uint32_t) (jr * RW) * 8, a, b);
-                        sts2(pq_s + (uint32_t) (jr * TXV) * 8, a[0], a[1]);
-                        sts2(pq_s + PQB + (uint32_t) (jr * TXV) * 8, b[0], b[1]);
+                        xmul(win[i & 1], a, b);
+                        const uint32_t dst = pq_s + (uint32_t) (row_of(i) * TXV) * 8;
+                        if (i < NPT) {
+                            pr[i][0] = a[0]; pr[i][1] = a[1];
+                            qr[i][0] = b[0]; qr[i][1] = b[1];
+                            if (i < P || i >= NPT - P) {
+                                sts2(dst, a[0], a[1]);
+                                sts2(dst + PQB, b[0], b[1]);
+                            }
+                        } else if (w + (i - NPT) * NWARP < 2 * P) {
+                            sts2(dst, a[0], a[1]);
+                            sts2(dst + PQB, b[0], b[1]);
+                        }
                     }
                 }
                 __syncthreads();
                 // the raw stage is free again: fetch plane q + NSTAGE into it
                 if (tid == 0 && q + NSTAGE < NP) issue(q + NSTAGE, stage);
 
-                // y product: extended column e = 0 .. NPT+2P-1 is tile row w*NPT + e; e in [P, P+NPT) is own
-                double pc[NPT + 2 * P][2], qc[NPT + 2 * P][2];
-#pragma unroll
-                for (int e = 0; e < NPT + 2 * P; ++e) {
-                    if (e >= P && e < P + NPT) {
-                        pc[e][0] = pr[e - P][0]; pc[e][1] = pr[e - P][1];
-                        qc[e][0] = qr[e - P][0]; qc[e][1] = qr[e - P][1];
-                    } else {
-                        const double2 a = lds2(pq_s + (uint32_t) ((w * NPT + e) * TXV) * 8);
-                        const double2 b = lds2(pq_s + PQB + (uint32_t) ((w * NPT + e) * TXV) * 8);
-                        pc[e][0] = a.x; pc[e][1] = a.y;
-                        qc[e][0] = b.x; qc[e][1] = b.y;
-                    }
-                }
+                // y product, input row by input row (each feeds up to 2P+1 output rows: independent chains).
+                // Extended column e = 0 .. NPT+2P-1 is tile row w*NPT + e; e in [P, P+NPT) is an own row
+                // (registers), the others are read back from shared.  Own rows go first: their operands
+                // are there while the halo loads are still in flight.
                 double G[NPT][2], H[NPT][2];
 #pragma unroll
-                for (int r = 0; r < NPT; ++r) {
+                for (int r = 0; r < NPT; ++r) G[r][0] = G[r][1] = H[r][0] = H[r][1] = 0.0;
+                double hp[2 * P][2], hq[2 * P][2];
+#pragma unroll
+                for (int i = 0; i < 2 * P; ++i) {
+                    const int e = i < P ? i : NPT + i;
+                    const double2 a = lds2(pq_s + (uint32_t) ((w * NPT + e) * TXV) * 8);
+                    const double2 b = lds2(pq_s + PQB + (uint32_t) ((w * NPT + e) * TXV) * 8);
+                    hp[i][0] = a.x; hp[i][1] = a.y;
+                    hq[i][0] = b.x; hq[i][1] = b.y;
+                }
+                auto yrow = [&](int e, const double (&pe)[2], const double (&qe)[2]) {
+                    double2 cy[W];
 #pragma unroll
                     for (int m = 0; m < W; ++m) {
-                        const double2 cy = lds2(yc_u + (uint32_t) (((w * NPT + r) * W + m) * 16));
+                        const int r = e - m;
+                        if (r >= 0 && r < NPT) cy[m] = lds2(yc_u + (uint32_t) (((w * NPT + r) * W + m) * 16));
+                    }
 #pragma unroll
-                        for (int xb = 0; xb < 2; ++xb) {
-                            if (m == 0) {
-                                G[r][xb] = cy.x * pc[r][xb];
-                                H[r][xb] = cy.x * qc[r][xb];
-                            } else {
-                                G[r][xb] = fma(cy.x, pc[r + m][xb], G[r][xb]);
-                                H[r][xb] = fma(cy.x, qc[r + m][xb], H[r][xb]);
+                    for (int m = 0; m < W; ++m) {
+                        const int r = e - m;
+                        if (r >= 0 && r < NPT) {
+#pragma unroll
+                            for (int xb = 0; xb < 2; ++xb) {
+                                G[r][xb] = fma(cy[m].x, pe[xb], G[r][xb]);
+                                H[r][xb] = fma(cy[m].x, qe[xb], H[r][xb]);
+                                G[r][xb] = fma(cy[m].y, qe[xb], G[r][xb]);
                             }
-                            G[r][xb] = fma(cy.y, qc[r + m][xb], G[r][xb]);
                         }
                     }
-                }
+                };
+#pragma unroll
+                for (int r = 0; r < NPT; ++r) yrow(P + r, pr[r], qr[r]);
+#pragma unroll
+                for (int i = 0; i < 2 * P; ++i) yrow(i < P ? i : NPT + i, hp[i], hq[i]);
                 // z product: scatter plane q onto the 2P+1 output planes it feeds
 #pragma unroll
                 for (int d = 0; d < W; ++d) {
@@ -285,7 +305,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
                     for (int r = 0; r < NPT; ++r) {
                         if (o_row[r] >= 0) {
                             double v0 = acc[r][0][j], v1 = acc[r][1][j];
-                            if (f_pl) {
+                            if (FORCING) {
                                 const double2 f = __ldg(reinterpret_cast<const double2*>(f_pl + o_row[r]));
                                 v0 = fma(g.gamma, f.x, v0);
                                 v1 = fma(g.gamma, f.y, v1);
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
                         }
                     }
                     o_pl += g.so[2];
-                    if (f_pl) f_pl += g.so[2];
+                    if (FORCING) f_pl += g.so[2];
                 }
 #pragma unroll
                 for (int r = 0; r < NPT; ++r) {
@@ -324,7 +344,7 @@ int sm_count_tma() {
 template <int P, int NPT, int NWARP, int NSTAGE, int MINB>
 int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
     using C = Cfg<P, NPT, NWARP, NSTAGE>;
-    auto kern = rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB>;
+    auto kern = g.forcing ? rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB, true> : rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB, false>;
     CUtensorMap map;
     const unsigned long long dims[3] = {(unsigned long long) g.in_n[0], (unsigned long long) g.in_n[1],
                                         (unsigned long long) g.in_n[2]};
