@@ -76,6 +76,8 @@ _SIGNATURES = {
     "adsb_create": (c_int, [c_int, ip, ip, ip, c_int, ctypes.POINTER(vp)]),
     "adsb_destroy": (c_int, [vp]),
     "adsb_set_stream": (c_int, [vp, vp]),
+    "adsb_set_sm_limit": (c_int, [vp, c_int]),
+    "adsb_copy2d": (c_int, [vp, vp, c_ll, vp, c_ll, c_ll, c_ll]),
     "adsb_synchronize": (c_int, [vp]),
     "adsb_set_axis_tables": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, dp, dp, dp, dp, ip]),
     "adsb_set_axis_factor": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_int, dp, ip]),

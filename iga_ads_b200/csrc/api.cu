@@ -59,6 +59,7 @@ struct adsb_ctx {
     std::vector<cudaEvent_t> free_events;
     double acc_ms[5] = {};
     long long launches = 0;
+    int sm_limit = 0;  // adsb_set_sm_limit
     size_t local_size() const { return (size_t) cnt[0] * cnt[1] * cnt[2]; }
 };
 
@@ -203,6 +204,7 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     G.s0_out = vo.s[l0];
     G.s1_in = vi.s[l1];
     G.s1_out = vo.s[l1];
+    G.max_ctas = c->sm_limit;
     G.pitch = F.n + (F.n & 1);
     if (G.pitch % 4 == 0) G.pitch += 2;  // pitch = 2 (mod 4): conflict-free 128-bit column access
     G.bulk = 0;
@@ -349,6 +351,7 @@ int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view&
     }
     g.alpha = f.alpha;
     g.gamma = f.gamma;
+    g.max_sms = c->sm_limit;
     StageTimer t(c, 0);
     int nl = 1;
     cudaError_t e = (cudaError_t) launch_rhs_collapsed(c->ndim, ops, g, c->stream, &nl);
@@ -435,6 +438,23 @@ int adsb_destroy(adsb_ctx* c) {
     }
     for (auto e : c->free_events) cudaEventDestroy(e);
     delete c;
+    return ADSB_OK;
+}
+
+int adsb_set_sm_limit(adsb_ctx* c, int sms) {
+    if (!c || sms < 0) return fail(ADSB_EINVAL, "set_sm_limit: bad argument");
+    c->sm_limit = sms;
+    return ADSB_OK;
+}
+
+int adsb_copy2d(adsb_ctx* c, void* dst, long long dpitch, const void* src, long long spitch, long long width,
+                long long height) {
+    if (!c || !dst || !src || width < 0 || height < 0 || dpitch < width || spitch < width)
+        return fail(ADSB_EINVAL, "copy2d: bad argument");
+    if (int rc = select_device(c)) return rc;
+    if (width == 0 || height == 0) return ADSB_OK;
+    CU(cudaMemcpy2DAsync(dst, (size_t) dpitch, src, (size_t) spitch, (size_t) width, (size_t) height, cudaMemcpyDefault,
+                         c->stream));
     return ADSB_OK;
 }
 

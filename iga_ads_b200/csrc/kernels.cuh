@@ -9,7 +9,7 @@ namespace adsb {
 constexpr int SWEEP_CH = 18;  // columns per chunk (one chunk per thread, held in registers)
 constexpr int SWEEP_RL = 2;   // lines per thread: they share every coefficient load and interleave for ILP
 constexpr int SWEEP_MAX_DEPTH_DEV = 6;
-constexpr int SWEEP_MAX_BOXES = 16;      // TMA boxes per tile and direction (tile-streaming sweep kernel)  // == SWEEP_MAX_DEPTH of internal.hpp
+constexpr int SWEEP_MAX_BOXES = 32;      // TMA boxes per tile and direction (tile-streaming sweep kernel)  // == SWEEP_MAX_DEPTH of internal.hpp
 
 // One factorised band matrix, prepared by build_sweep_plan (host_setup.cpp).
 struct SweepFactor {
@@ -38,6 +38,7 @@ struct SweepGeom {
     int L0, L1;
     int pitch;  // CONTIG: shared-memory row pitch in doubles (even)
     int bulk;   // CONTIG: rows are 16 B aligned on both sides -> TMA bulk copies
+    int max_ctas;  // persistent kernels: at most this many CTAs (0: one per SM)
 };
 
 // Tile-streaming variant (kernels_sweep_tile.cu): persistent CTAs, TMA-fed shared-memory ring.
@@ -87,11 +88,12 @@ struct RhsGeom {
     int in_lo[3], in_n[3];    // box covered by `in` in global indices
     int out_lo[3], out_n[3];  // box to produce
     double alpha, beta[3], gamma;
+    int max_sms;  // launch heuristics assume this many SMs (0: the whole device)
 };
 // *nlaunch (optional) receives the number of kernels launched
 int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStream_t st, int* nlaunch = nullptr);
 // TMA-fed 3-D variant (kernels_rhs_tma.cu).  0: launched; -1: not eligible; otherwise a cudaError_t.
-int launch_rhs_tma(const RhsOps& ops, const RhsGeom& G, cudaStream_t st);
+int launch_rhs_tma(const RhsOps& ops, const RhsGeom& G, cudaStream_t st, bool narrow = false);
 // Encode a 3-D FP64 tiled tensor map (element strides of dims 1 and 2; dim 0 is contiguous) into *map
 // (a CUtensorMap, 128 bytes, 64 B aligned).  False when the driver entry point is missing or refuses.
 bool encode_tensor_map3(void* map, const double* base, const unsigned long long dims[3],

@@ -491,7 +491,8 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
             // count that minimises (waves of resident CTAs) x (planes per CTA)
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NTH, smem);
-            const long long slots = (long long) sm_count() * (per_sm > 0 ? per_sm : 1);
+            const int sms = (g.max_sms > 0 && g.max_sms < sm_count()) ? g.max_sms : sm_count();
+            const long long slots = (long long) sms * (per_sm > 0 ? per_sm : 1);
             const long long tiles = (long long) tx * ty;
             long long best = -1;
             for (int ns = 1; ns <= 64 && ns <= g.out_n[2]; ++ns) {
@@ -512,6 +513,7 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
     };
     int rc = -1;
     if (ndim == 3 && try_tma) rc = launch_rhs_tma(ops, g, st);  // -1: not eligible
+    const bool used_tma = rc != -1;
     if (rc != -1)
         ;
     else if (ndim == 3)
@@ -527,6 +529,10 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
     e.out_n[0] = rem;
     e.out = g0.out + g.out_n[0];
     if (g0.forcing) e.forcing = g0.forcing + g.out_n[0];
+    if (used_tma) {  // the same kernel with 8-pair-wide warps; -1: not eligible (odd remainder, ...)
+        rc = launch_rhs_tma(ops, e, st, true);
+        if (rc != -1) return rc;
+    }
     const long long cols = (long long) rem * e.out_n[1];
     dim3 eb(128, 1, 1), eg((unsigned) ((cols + 127) / 128), ndim == 3 ? (e.out_n[2] + EDGE_ZSEG - 1) / EDGE_ZSEG : 1, 1);
     if (ndim == 3)

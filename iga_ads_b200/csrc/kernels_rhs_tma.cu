@@ -29,13 +29,16 @@ namespace adsb {
 
 namespace {
 
-constexpr int TXV = 64;  // tile width in DOFs: 32 lanes x 2
-
-template <int P, int NPT, int NWARP, int NSTAGE>
+// XP = x pairs per tile row: a warp is XP lanes wide and 32/XP row groups tall.  XP = 32 is the work
+// horse (tile 64 DOFs wide); XP = 8 serves the narrow x remainder of the 64-wide tiling (<= 16 columns).
+template <int P, int NPT, int NWARP, int NSTAGE, int XP>
 struct Cfg {
+    static_assert(XP == 32 || XP == 8, "lane layouts with conflict-free 128-bit shared accesses");
     static constexpr int W = 2 * P + 1;
     static constexpr int PH = P + (P & 1);   // x halo rounded up to even: 16 B aligned windows
-    static constexpr int TY = NWARP * NPT;   // output rows per tile
+    static constexpr int TXV = 2 * XP;       // tile width in DOFs
+    static constexpr int RG = 32 / XP;       // row groups per warp
+    static constexpr int TY = NWARP * RG * NPT;  // output rows per tile
     static constexpr int UH = TY + 2 * P;    // rows of the raw / P / Q tiles
     static constexpr int RW = TXV + 2 * PH;  // raw row length in doubles
     static constexpr int NTH = NWARP * 32;
@@ -44,7 +47,7 @@ struct Cfg {
     static constexpr int PQ_BYTES = UH * TXV * 8;                       // one P (or Q) tile
     static constexpr int YC_BYTES = TY * W * 16;                        // [TY][W] (My, -beta_y Sy)
     static constexpr int FIXED_BYTES = NSTAGE * RAW_STRIDE + 4 * PQ_BYTES + YC_BYTES + NSTAGE * 8 + 8 + 128;
-    static constexpr int NHALO = (2 * P + NWARP - 1) / NWARP;           // halo rows a warp may have to do
+    static constexpr int NHALO = (2 * P * XP + NTH - 1) / NTH;          // halo-row x products a thread may have to do
 };
 
 __device__ __forceinline__ double2 lds2(uint32_t a) {
@@ -78,11 +81,11 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-template <int P, int NPT, int NWARP, int NSTAGE, int MINB, bool FORCING>
+template <int P, int NPT, int NWARP, int NSTAGE, int MINB, bool FORCING, int XP>
 __global__ void __launch_bounds__(NWARP * 32, MINB)
     rhs_tma_kernel(const __grid_constant__ CUtensorMap tmap, const RhsOps ops, const RhsGeom g, int zseg) {
-    using C = Cfg<P, NPT, NWARP, NSTAGE>;
-    constexpr int W = C::W, PH = C::PH, TY = C::TY, UH = C::UH, RW = C::RW, NTH = C::NTH;
+    using C = Cfg<P, NPT, NWARP, NSTAGE, XP>;
+    constexpr int W = C::W, PH = C::PH, TY = C::TY, UH = C::UH, RW = C::RW, NTH = C::NTH, TXV = C::TXV;
     constexpr uint32_t RAWS = C::RAW_STRIDE, PQB = C::PQ_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base_u = (smem_addr(smem_raw) + 127u) & ~127u;
@@ -96,7 +99,9 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(base_p + (bar_u - base_u));
     double2* zt = reinterpret_cast<double2*>(base_p + (zt_u - base_u));
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x;
+    const int lx = tid % XP;   // x pair of this thread inside the tile row
+    const int rg = tid / XP;   // its row group: rows rg*NPT .. rg*NPT + NPT-1 of the tile
     const int x0 = g.out_lo[0] + blockIdx.x * TXV;
     const int y0 = g.out_lo[1] + blockIdx.y * TY;
     const int nx = ops.n[0], ny = ops.n[1];
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
     double kx[2][W], mx[2][W];
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-        const int gxc = min(x0 + 2 * lane + b, nx - 1);
+        const int gxc = min(x0 + 2 * lx + b, nx - 1);
 #pragma unroll
         for (int m = 0; m < W; ++m) {
             const double a = ops.Mx[gxc * W + m], s = ops.Sx[gxc * W + m];
@@ -163,17 +168,17 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
             }
         }
     };
-    const uint32_t lane_raw = (uint32_t) (2 * lane) * 8;  // column offset of the lane's window in a raw row
-    const uint32_t lane_pq = (uint32_t) (2 * lane) * 8;   // ... of its pair in a P/Q row
-    const int jown = P + w * NPT;                         // first own row (tile row index, 0 = y0 - P)
+    const uint32_t lane_raw = (uint32_t) (2 * lx) * 8;  // column offset of the thread's window in a raw row
+    const uint32_t lane_pq = (uint32_t) (2 * lx) * 8;   // ... of its pair in a P/Q row
+    const int jown = P + rg * NPT;                      // first own row (tile row index, 0 = y0 - P)
 
     // outputs of this thread: NPT row pairs; offsets inside a plane + marching plane pointers
-    const int gx = x0 + 2 * lane;
+    const int gx = x0 + 2 * lx;
     const int xend = g.out_lo[0] + g.out_n[0];
     int o_row[NPT];  // -1: nothing to store
 #pragma unroll
     for (int r = 0; r < NPT; ++r) {
-        const int gy = y0 + w * NPT + r;
+        const int gy = y0 + rg * NPT + r;
         const bool ok = gy < g.out_lo[1] + g.out_n[1] && gx < xend;
         o_row[r] = ok ? (int) ((gx - g.out_lo[0]) + (long long) (gy - g.out_lo[1]) * g.so[1]) : -1;
     }
@@ -206,10 +211,12 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
                 // in between would otherwise pin every load behind them).
                 double pr[NPT][2], qr[NPT][2];
                 {
-                    constexpr int NXR = NPT + C::NHALO;  // rows of this thread: own rows, then its halo rows
+                    // rows of this thread: own rows, then its share of the 2P halo rows of the tile (P above, P
+                    // below; halo task t = row t / XP, pair t % XP = lx)
+                    constexpr int NXR = NPT + C::NHALO;
                     auto row_of = [&](int i) -> int {    // tile row of the i-th of them
                         if (i < NPT) return jown + i;
-                        const int h = min(w + (i - NPT) * NWARP, 2 * P - 1);  // surplus warps shadow the last halo row
+                        const int h = min((tid + (i - NPT) * NTH) / XP, 2 * P - 1);  // surplus threads shadow the last halo row
                         return h < P ? h : TY + h;
                     };
                     double win[2][2 * PH + 2];
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
                                 sts2(dst, a[0], a[1]);
                                 sts2(dst + PQB, b[0], b[1]);
                             }
-                        } else if (w + (i - NPT) * NWARP < 2 * P) {
+                        } else if (tid + (i - NPT) * NTH < 2 * P * XP) {
                             sts2(dst, a[0], a[1]);
                             sts2(dst + PQB, b[0], b[1]);
                         }
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
                 if (tid == 0 && q + NSTAGE < NP) issue(q + NSTAGE, stage);
 
                 // y product, input row by input row (each feeds up to 2P+1 output rows: independent chains).
-                // Extended column e = 0 .. NPT+2P-1 is tile row w*NPT + e; e in [P, P+NPT) is an own row
+                // Extended column e = 0 .. NPT+2P-1 is tile row rg*NPT + e; e in [P, P+NPT) is an own row
                 // (registers), the others are read back from shared.  Own rows go first: their operands
                 // are there while the halo loads are still in flight.
                 double G[NPT][2], H[NPT][2];
@@ -257,8 +264,8 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
 #pragma unroll
                 for (int i = 0; i < 2 * P; ++i) {
                     const int e = i < P ? i : NPT + i;
-                    const double2 a = lds2(pq_s + (uint32_t) ((w * NPT + e) * TXV) * 8);
-                    const double2 b = lds2(pq_s + PQB + (uint32_t) ((w * NPT + e) * TXV) * 8);
+                    const double2 a = lds2(pq_s + (uint32_t) ((rg * NPT + e) * TXV) * 8);
+                    const double2 b = lds2(pq_s + PQB + (uint32_t) ((rg * NPT + e) * TXV) * 8);
                     hp[i][0] = a.x; hp[i][1] = a.y;
                     hq[i][0] = b.x; hq[i][1] = b.y;
                 }
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
 #pragma unroll
                     for (int m = 0; m < W; ++m) {
                         const int r = e - m;
-                        if (r >= 0 && r < NPT) cy[m] = lds2(yc_u + (uint32_t) (((w * NPT + r) * W + m) * 16));
+                        if (r >= 0 && r < NPT) cy[m] = lds2(yc_u + (uint32_t) (((rg * NPT + r) * W + m) * 16));
                     }
 #pragma unroll
                     for (int m = 0; m < W; ++m) {
@@ -341,10 +348,12 @@ int sm_count_tma() {
     return n;
 }
 
-template <int P, int NPT, int NWARP, int NSTAGE, int MINB>
+template <int P, int NPT, int NWARP, int NSTAGE, int MINB, int XP = 32>
 int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
-    using C = Cfg<P, NPT, NWARP, NSTAGE>;
-    auto kern = g.forcing ? rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB, true> : rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB, false>;
+    using C = Cfg<P, NPT, NWARP, NSTAGE, XP>;
+    constexpr int TXV = C::TXV;
+    auto kern = g.forcing ? rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB, true, XP>
+                          : rhs_tma_kernel<P, NPT, NWARP, NSTAGE, MINB, false, XP>;
     CUtensorMap map;
     const unsigned long long dims[3] = {(unsigned long long) g.in_n[0], (unsigned long long) g.in_n[1],
                                         (unsigned long long) g.in_n[2]};
@@ -358,7 +367,8 @@ int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
     if (zcap < 8 * P) return -1;
     // z segments: every segment re-reads 2P halo planes and pays a pipeline prologue; choose the count
     // that minimises (waves of resident CTAs) x (planes per CTA)
-    const long long slots = (long long) sm_count_tma() * MINB;
+    const int sms = (g.max_sms > 0 && g.max_sms < sm_count_tma()) ? g.max_sms : sm_count_tma();
+    const long long slots = (long long) sms * MINB;
     const long long tiles = (long long) tx * ty;
     long long best = -1;
     int zseg = 1;
@@ -386,7 +396,8 @@ int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
 }  // namespace
 
 // 0: launched; -1: this problem is not eligible (caller uses the cp.async kernel); else a cudaError_t.
-int launch_rhs_tma(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
+// narrow: the output box is at most 16 columns wide (x remainder of the 64-wide tiling): 8-pair-wide warps.
+int launch_rhs_tma(const RhsOps& ops, const RhsGeom& g, cudaStream_t st, bool narrow) {
     const int p = ops.p[0];
     if (ops.p[1] != p || ops.p[2] != p) return -1;
     auto even = [](long long v) { return (v & 1) == 0; };
@@ -400,6 +411,14 @@ int launch_rhs_tma(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
         const char* e = getenv("ADSB_RHS_TMA_VARIANT");
         return e ? atoi(e) : 0;
     }();
+    if (narrow) {
+        if (g.out_n[0] > 16) return -1;
+        switch (p) {
+        case 2: return launch_cfg<2, 4, 4, 3, 2, 8>(ops, g, st);
+        case 3: return launch_cfg<3, 2, 6, 3, 1, 8>(ops, g, st);
+        default: return -1;
+        }
+    }
     switch (p) {
     case 2:
         if (variant == 1) return launch_cfg<2, 4, 4, 4, 2>(ops, g, st);

@@ -410,7 +410,8 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
         return v;
     }();
     dim3 block(ncons + 32, 1, 1);
-    dim3 grid(T.ntiles < sms ? T.ntiles : sms, 1, 1);
+    const int cap = (G.max_ctas > 0 && G.max_ctas < sms) ? G.max_ctas : sms;
+    dim3 grid(T.ntiles < cap ? T.ntiles : cap, 1, 1);
     k<<<grid, block, smem, st>>>(F, T);
     return (int) cudaGetLastError();
 }

@@ -51,6 +51,14 @@ class Context:
     def set_stream(self, stream_ptr):
         check(self.lib.adsb_set_stream(self.h, ctypes.c_void_p(stream_ptr)))
 
+    def set_sm_limit(self, sms):
+        check(self.lib.adsb_set_sm_limit(self.h, int(sms)))
+
+    def copy2d(self, dst_ptr, dst_pitch, src_ptr, src_pitch, width, height):
+        """strided device copy on this context's stream; all sizes in bytes except `height` (rows)"""
+        check(self.lib.adsb_copy2d(self.h, ctypes.c_void_p(dst_ptr), dst_pitch, ctypes.c_void_p(src_ptr), src_pitch,
+                                   width, height))
+
     def synchronize(self):
         check(self.lib.adsb_synchronize(self.h))
 

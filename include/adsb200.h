@@ -93,6 +93,16 @@ int adsb_destroy(adsb_ctx* ctx);
 /* CUDA stream (cudaStream_t passed as void*) all later calls enqueue on; NULL = default stream. */
 int adsb_set_stream(adsb_ctx* ctx, void* cuda_stream);
 int adsb_synchronize(adsb_ctx* ctx);
+/* Cap the number of SMs the persistent sweep kernels occupy and the right-hand-side launch heuristics
+ * assume (0 = the whole device).  Lets a caller run two contexts on two streams side by side, e.g. a
+ * sweep whose stores travel over NVLink next to the compute of the following slab chunk.  No reference
+ * counterpart (the reference is single-threaded host code). */
+int adsb_set_sm_limit(adsb_ctx* ctx, int sms);
+/* Strided device-to-device copy on the context's stream (cudaMemcpy2DAsync, copy engines): `height` rows
+ * of `width_bytes`, row pitches in bytes.  dst may be peer memory mapped into this process -- the slab
+ * exchange of a sharded step moves its blocks with this while the SMs work on the next chunk. */
+int adsb_copy2d(adsb_ctx* ctx, void* dst, long long dst_pitch_bytes, const void* src, long long src_pitch_bytes,
+                long long width_bytes, long long height);
 
 /* Upload one axis' quadrature tables (layout of adsb_basis_tables); the library derives the 1-D
  * Gram / stiffness / advection operators from them by the same quadrature.

@@ -59,6 +59,15 @@ def _worker(rank, world, port, n, p, q):
         send = torch.from_numpy(plan.emulate_pack(1, got))
         back = plan.emulate_unpack(1, _all_to_all(send, plan, rank, world).numpy())  # [z_local][y][x]
         ok2 = np.array_equal(back, full[z0:z0 + cz])
+        # the chunked block layout of the copy-engine exchange (one contiguous piece per chunk and peer)
+        for nchunk in (2, 3):
+            blk = plan.chunking(2, nchunk)[2]
+            send = torch.from_numpy(plan.emulate_pack_chunked(2, full[z0:z0 + cz], nchunk))
+            everything = [torch.zeros_like(send) for _ in range(world)]
+            dist.all_gather(everything, send)
+            recv = torch.cat([everything[r][rank * blk:(rank + 1) * blk] for r in range(world)])
+            got = plan.emulate_unpack_chunked(2, recv.numpy(), nchunk)
+            ok1 = ok1 and np.array_equal(got, want)
         q.put((rank, ok1, ok2))
     finally:
         dist.destroy_process_group()
