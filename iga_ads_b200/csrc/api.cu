@@ -60,6 +60,7 @@ struct adsb_ctx {
     double acc_ms[5] = {};
     long long launches = 0;
     int sm_limit = 0;  // adsb_set_sm_limit
+    RhsSide side;      // second stream + events for the x-remainder kernel of the right-hand side (lazy)
     size_t local_size() const { return (size_t) cnt[0] * cnt[1] * cnt[2]; }
 };
 
@@ -354,7 +355,12 @@ int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view&
     g.max_sms = c->sm_limit;
     StageTimer t(c, 0);
     int nl = 1;
-    cudaError_t e = (cudaError_t) launch_rhs_collapsed(c->ndim, ops, g, c->stream, &nl);
+    if (!c->side.side) {
+        CU(cudaStreamCreateWithFlags(&c->side.side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->side.fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->side.join, cudaEventDisableTiming));
+    }
+    cudaError_t e = (cudaError_t) launch_rhs_collapsed(c->ndim, ops, g, c->stream, &nl, &c->side);
     if (e != cudaSuccess) return cuda_fail(e, "rhs kernel launch");
     c->launches += nl;
     return ADSB_OK;
@@ -437,6 +443,11 @@ int adsb_destroy(adsb_ctx* c) {
         cudaEventDestroy(s.b);
     }
     for (auto e : c->free_events) cudaEventDestroy(e);
+    if (c->side.side) {
+        cudaStreamDestroy(c->side.side);
+        cudaEventDestroy(c->side.fork);
+        cudaEventDestroy(c->side.join);
+    }
     delete c;
     return ADSB_OK;
 }

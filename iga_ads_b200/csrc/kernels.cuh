@@ -90,8 +90,15 @@ struct RhsGeom {
     double alpha, beta[3], gamma;
     int max_sms;  // launch heuristics assume this many SMs (0: the whole device)
 };
+// Optional second stream + two events: the narrow x-remainder kernel is forked onto `side` so it runs
+// next to the main kernel (it fills the CTA slots the main grid leaves free) and joined back into st.
+struct RhsSide {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
 // *nlaunch (optional) receives the number of kernels launched
-int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStream_t st, int* nlaunch = nullptr);
+int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStream_t st, int* nlaunch = nullptr,
+                         const RhsSide* side = nullptr);
 // TMA-fed 3-D variant (kernels_rhs_tma.cu).  0: launched; -1: not eligible; otherwise a cudaError_t.
 int launch_rhs_tma(const RhsOps& ops, const RhsGeom& G, cudaStream_t st, bool narrow = false);
 // Encode a 3-D FP64 tiled tensor map (element strides of dims 1 and 2; dim 0 is contiguous) into *map

@@ -465,7 +465,8 @@ int sm_count() {
 }
 
 template <int P, int NPT, int NWARP, int MINB, bool YREG>
-int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bool try_tma, int* nlaunch) {
+int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bool try_tma, int* nlaunch,
+             const RhsSide* side) {
     using T = RhsTile<P, NPT, NWARP>;
     if (g0.si[0] != 1 || g0.so[0] != 1) return (int) cudaErrorInvalidValue;  // x must be contiguous
     // x remainder of the 64-wide tiling: a nearly empty tile column would cost a full one, so a
@@ -512,6 +513,8 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
         return (int) cudaGetLastError();
     };
     int rc = -1;
+    const bool fork = split && side && side->side && ndim == 3 && try_tma;
+    if (fork && cudaEventRecord(side->fork, st) != cudaSuccess) return (int) cudaGetLastError();
     if (ndim == 3 && try_tma) rc = launch_rhs_tma(ops, g, st);  // -1: not eligible
     const bool used_tma = rc != -1;
     if (rc != -1)
@@ -529,17 +532,30 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
     e.out_n[0] = rem;
     e.out = g0.out + g.out_n[0];
     if (g0.forcing) e.forcing = g0.forcing + g.out_n[0];
-    if (used_tma) {  // the same kernel with 8-pair-wide warps; -1: not eligible (odd remainder, ...)
-        rc = launch_rhs_tma(ops, e, st, true);
-        if (rc != -1) return rc;
-    }
     const long long cols = (long long) rem * e.out_n[1];
     dim3 eb(128, 1, 1), eg((unsigned) ((cols + 127) / 128), ndim == 3 ? (e.out_n[2] + EDGE_ZSEG - 1) / EDGE_ZSEG : 1, 1);
-    if (ndim == 3)
-        rhs_edge_kernel<P, true><<<eg, eb, 0, st>>>(ops, e);
-    else
-        rhs_edge_kernel<P, false><<<eg, eb, 0, st>>>(ops, e);
-    return (int) cudaGetLastError();
+    // the remainder kernel may run next to the main kernel on the caller's side stream (fork / join)
+    const bool forked = fork && used_tma;
+    cudaStream_t es = forked ? side->side : st;
+    if (forked) {
+        cudaError_t ce = cudaStreamWaitEvent(side->side, side->fork, 0);
+        if (ce != cudaSuccess) return (int) ce;
+    }
+    rc = -1;
+    if (used_tma) rc = launch_rhs_tma(ops, e, es, true);  // same kernel, 8-pair-wide warps; -1: not eligible
+    if (rc == -1) {
+        if (ndim == 3)
+            rhs_edge_kernel<P, true><<<eg, eb, 0, es>>>(ops, e);
+        else
+            rhs_edge_kernel<P, false><<<eg, eb, 0, es>>>(ops, e);
+        rc = (int) cudaGetLastError();
+    }
+    if (forked) {
+        cudaError_t ce = cudaEventRecord(side->join, side->side);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, side->join, 0);
+        if (ce != cudaSuccess) return (int) ce;
+    }
+    return rc;
 }
 
 __global__ void set_plane_kernel(double* t, long long sa, long long sb, int na, int nb, const double* values) {
@@ -550,7 +566,8 @@ __global__ void set_plane_kernel(double* t, long long sa, long long sb, int na, 
 
 }  // namespace
 
-int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& g, cudaStream_t st, int* nlaunch) {
+int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& g, cudaStream_t st, int* nlaunch,
+                         const RhsSide* side) {
     const int p = ops.p[0];
     if (ops.p[1] != p || (ndim == 3 && ops.p[2] != p)) return (int) cudaErrorInvalidValue;
     // ADSB_RHS_VARIANT: 0 = TMA-fed kernel where eligible (kernels_rhs_tma.cu), else the cp.async kernel;
@@ -561,16 +578,16 @@ int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& g, cudaStre
     }();
     const bool tma = variant < 10;
     switch (p) {
-    case 1: return launch_p<1, 2, 8, 2, false>(ndim, ops, g, st, tma, nlaunch);
+    case 1: return launch_p<1, 2, 8, 2, false>(ndim, ops, g, st, tma, nlaunch, side);
     case 2:
         // cp.async kernel, measured at 514^3 on B200: 0.93 ms (8 warps, 1 CTA/SM, y rows in registers), 1.02
         // (variant 11: 2 CTAs/SM, y rows broadcast from shared), 1.11 (variant 12: 12 warps)
-        if (variant == 11) return launch_p<2, 2, 8, 2, false>(ndim, ops, g, st, false, nlaunch);
-        if (variant == 12) return launch_p<2, 2, 12, 1, true>(ndim, ops, g, st, false, nlaunch);
-        return launch_p<2, 2, 8, 1, true>(ndim, ops, g, st, tma, nlaunch);
-    case 3: return launch_p<3, 1, 8, 2, false>(ndim, ops, g, st, tma, nlaunch);
-    case 4: return launch_p<4, 1, 8, 1, false>(ndim, ops, g, st, tma, nlaunch);
-    case 5: return launch_p<5, 1, 8, 1, false>(ndim, ops, g, st, tma, nlaunch);
+        if (variant == 11) return launch_p<2, 2, 8, 2, false>(ndim, ops, g, st, false, nlaunch, side);
+        if (variant == 12) return launch_p<2, 2, 12, 1, true>(ndim, ops, g, st, false, nlaunch, side);
+        return launch_p<2, 2, 8, 1, true>(ndim, ops, g, st, tma, nlaunch, side);
+    case 3: return launch_p<3, 1, 8, 2, false>(ndim, ops, g, st, tma, nlaunch, side);
+    case 4: return launch_p<4, 1, 8, 1, false>(ndim, ops, g, st, tma, nlaunch, side);
+    case 5: return launch_p<5, 1, 8, 1, false>(ndim, ops, g, st, tma, nlaunch, side);
     default: return (int) cudaErrorInvalidValue;
     }
 }

@@ -77,21 +77,30 @@ __global__ void __launch_bounds__(288, 1)
             mbar_init(&full[b], 1);
             mbar_init(&done[b], 1);
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // rows the TMA never writes stay zero for the whole kernel (chunks may read past the line end)
-    for (int i = tid; i < G.nbuf * tile_doubles; i += blockDim.x) tiles[i] = 0.0;
-    // the factor's tables: every tile of this persistent CTA uses them
-    for (int i = tid; i < rows * LF; i += blockDim.x) s_cfF[i] = F0.cfF[i];
-    for (int i = tid; i < rows * LB; i += blockDim.x) s_cfB[i] = F0.cfB[i];
-    for (int i = tid; i < rows * LC; i += blockDim.x) s_cfC[i] = F0.cfC[i];
-    for (int i = tid; i < SC * KL * KL; i += blockDim.x) s_T[i] = F0.T[i];
-    for (int i = tid; i < SC * KD * KD; i += blockDim.x) s_Rm[i] = F0.Rm[i];
-    for (int i = tid; i < SC * (MD - 1) * KL * KL; i += blockDim.x) s_W[i] = F0.W[i];
-    for (int i = tid; i < SC * (MD - 1) * KD * KD; i += blockDim.x) s_V[i] = F0.V[i];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     const int my_count = (G.ntiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+
+    if (tid < ncons) {
+        // consumers set the CTA up while the producer's first loads are already in flight:
+        // STRIDED: rows [n, rows_needed) of every ring slot are never written by the TMA and must read as
+        // zero (chunks read past the line end); CONTIG reads are guarded, nothing to clear
+        if (!CONTIG) {
+            const int pad0 = n * NL, pad = tile_doubles - pad0;
+            for (int i = tid; i < G.nbuf * pad; i += ncons) tiles[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
+        }
+        // the factor's tables: every tile of this persistent CTA uses them
+        for (int i = tid; i < rows * LF; i += ncons) s_cfF[i] = F0.cfF[i];
+        for (int i = tid; i < rows * LB; i += ncons) s_cfB[i] = F0.cfB[i];
+        for (int i = tid; i < rows * LC; i += ncons) s_cfC[i] = F0.cfC[i];
+        for (int i = tid; i < SC * KL * KL; i += ncons) s_T[i] = F0.T[i];
+        for (int i = tid; i < SC * KD * KD; i += ncons) s_Rm[i] = F0.Rm[i];
+        for (int i = tid; i < SC * (MD - 1) * KL * KL; i += ncons) s_W[i] = F0.W[i];
+        for (int i = tid; i < SC * (MD - 1) * KD * KD; i += ncons) s_V[i] = F0.V[i];
+        sweep_sync(ncons);
+    }
 
     if (tid >= ncons) {
         // ------------------------------------------------------------------ producer warp

@@ -257,7 +257,9 @@ class ShardedHeat3d:
         # chunks of >= 32 planes (the right-hand side re-reads 2p planes per chunk)
         self.nchunk = 1
         if world > 1 and mode in ("p2p", "ce"):
-            want = int(os.environ.get("ADSB_SHARDED_CHUNKS", "4" if mode == "ce" else "1"))
+            # measured on B200 (512^3): 2 chunks beat 1, 3 and 4 at 2, 4 and 8 GPUs -- every extra chunk costs
+            # ~0.08 ms of kernel ramp-up / halo planes, and only the last chunk's exchange is exposed
+            want = int(os.environ.get("ADSB_SHARDED_CHUNKS", "2" if mode == "ce" else "1"))
             min_planes = max(int(os.environ.get("ADSB_SHARDED_MIN_PLANES", "32")), max(p, 1))
             self.nchunk = max(1, min(want, min(self.plan.sizes[1] + self.plan.sizes[2]) // min_planes))
         # doubles per (src, dst) block: the chunked layout of the copy-engine exchange pads differently
@@ -301,6 +303,8 @@ class ShardedHeat3d:
             self.bg_sms = int(os.environ.get("ADSB_SHARDED_BG_SMS", "32"))
             self.sm_count = torch.cuda.get_device_properties(self.dev).multi_processor_count
             self.bg_stream = torch.cuda.Stream(device=self.dev)
+            # peer copies to different destinations go round-robin over a few streams (several copy engines)
+            self.copy_streams = [self.bg_stream] + [torch.cuda.Stream(device=self.dev) for _ in range(2)]
             self.ctx_bg = Context(self.n, device=device)   # same tables and factors, its own stream
             self.ctx_bg.set_stream(self.bg_stream.cuda_stream)
             for ax in range(3):
@@ -540,10 +544,12 @@ class ShardedHeat3d:
                                     _view(nout, v["send"][1]), off_out=self._ce_off[A, k, ci])
                 self._mark("sweep_b")
                 self._chunk_events[ci].record(main)
-                self.bg_stream.wait_event(self._chunk_events[ci])
+                for cs_ in self.copy_streams:
+                    cs_.wait_event(self._chunk_events[ci])
                 for step_to in range(1, self.world):
                     dst = (self.rank + step_to) % self.world
                     nbytes = 8 * plan.sizes[B][dst] * cc * nx
+                    self.ctx_bg.set_stream(self.copy_streams[step_to % len(self.copy_streams)].cuda_stream)
                     self.ctx_bg.copy2d(self.peers[dst] + 8 * (self.recv2_off[k] + self.rank * blk + ci * piece), nbytes,
                                        self.send.data_ptr() + 8 * (dst * blk + ci * piece), nbytes, nbytes, 1)
                 continue
@@ -554,7 +560,12 @@ class ShardedHeat3d:
             self.ctx_bg.sweep_view(B, 0, wk_ptr, _view(nout, v["work"][1]), recv.data_ptr() + 8 * cs * nx,
                                    _view(nout, v["send"][1]), off_out=self._p2p_off[A])
         self.ctx.set_sm_limit(0)
-        main.wait_stream(self.bg_stream)
+        if ce:
+            for cs_ in self.copy_streams:
+                main.wait_stream(cs_)
+            self.ctx_bg.set_stream(self.bg_stream.cuda_stream)
+        else:
+            main.wait_stream(self.bg_stream)
         self.exchange_bytes += 8 * c * (self.n[B] - plan.cnt(B)) * nx
         self._mark("exchange_tail")
         self.hdl.barrier(channel=0)
