@@ -121,66 +121,54 @@ class SlabPlan:
             off[k] = r * self.block + (k - self.starts[A][r]) * nx
         return off
 
-    # ---- chunked exchange layout (copy-engine exchange): the A-planes of a slab are cut into chunks of
-    # cc = ceil(cmax[A] / nchunk) planes; block (src r -> dst s) = [chunk][b_local of s][a in chunk][x], so
-    # what one chunk sends to one peer is ONE contiguous piece (strided peer copies are slow: ~1 us per row)
-    def chunking(self, A, nchunk):
-        """(planes per chunk, doubles per chunk piece, doubles per block)"""
-        B = 3 - A
-        cc = -(-self.cmax[A] // nchunk)
-        piece = self.cmax[B] * cc * self.n[0]
-        return cc, piece, nchunk * piece
-
-    def chunks_of(self, A, nchunk, rank=None):
-        """[(first local plane, planes)] of the non-empty chunks of a rank's slab"""
-        cc = self.chunking(A, nchunk)[0]
+    # ---- exchange layout of the copy-engine path: block (src r -> dst s) = [a_local of r][b_local of s][x]
+    # (padded to cmax), i.e. the A-planes of the sender are the slowest index, so ANY range of planes -- a
+    # chunk -- is one contiguous piece per peer (strided peer copies are slow: ~1 us per row)
+    def chunks_of(self, A, fractions, rank=None):
+        """[(first local plane, planes)]: the slab cut at the given cumulative fractions of cmax[A]"""
         c = self.sizes[A][self.rank if rank is None else rank]
-        return [(i * cc, min(cc, c - i * cc)) for i in range(nchunk) if i * cc < c]
+        cuts = [0] + [min(c, int(round(f * self.cmax[A]))) for f in fractions] + [c]
+        cuts = sorted(set(cuts))
+        return [(lo, hi - lo) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
 
-    def pack_offsets_chunk(self, A, nchunk, ci):
-        """off_out[j] of the B sweep of chunk ci (relative to the send buffer); the line (x, a in chunk)
-        adds x + a*nx."""
+    def pack_offsets_t(self, A):
+        """off_out[j] of the B sweep (relative to the send buffer); the line (x, a_local) adds
+        x + a_local*cmax[B]*nx."""
         B, nx = 3 - A, self.n[0]
-        cc, piece, blk = self.chunking(A, nchunk)
         off = np.zeros(self.n[B], dtype=np.int64)
         for j in range(self.n[B]):
             s = self.owner(B, j)
-            off[j] = s * blk + ci * piece + (j - self.starts[B][s]) * cc * nx
+            off[j] = s * self.block + (j - self.starts[B][s]) * nx
         return off
 
-    def unpack_offsets_chunk(self, A, nchunk):
-        """off_in[k] of the A sweep reading the chunked receive blocks; the line (x, b_local) adds
-        x + b_local*cc*nx."""
-        nx = self.n[0]
-        cc, piece, blk = self.chunking(A, nchunk)
+    def unpack_offsets_t(self, A):
+        """off_in[k] of the A sweep reading the receive blocks; the line (x, b_local) adds x + b_local*nx."""
+        B, nx = 3 - A, self.n[0]
         off = np.zeros(self.n[A], dtype=np.int64)
         for k in range(self.n[A]):
             r = self.owner(A, k)
-            a = k - self.starts[A][r]
-            off[k] = r * blk + (a // cc) * piece + (a % cc) * nx
+            off[k] = r * self.block + (k - self.starts[A][r]) * self.cmax[B] * nx
         return off
 
-    def emulate_pack_chunked(self, A, work, nchunk):
-        """work [cnt(A)][n[B]][nx] -> flat send buffer in the chunked layout"""
+    def emulate_pack_t(self, A, work):
+        """work [cnt(A)][n[B]][nx] -> flat send buffer, blocks [a][b][x]"""
         B, nx = 3 - A, self.n[0]
-        send = np.zeros(self.world * self.chunking(A, nchunk)[2])
-        for ci, (cs, cn) in enumerate(self.chunks_of(A, nchunk)):
-            off = self.pack_offsets_chunk(A, nchunk, ci)
-            for a in range(cn):
-                for j in range(self.n[B]):
-                    o = off[j] + a * nx
-                    send[o:o + nx] = work[cs + a, j]
+        send = np.zeros(self.world * self.block)
+        off = self.pack_offsets_t(A)
+        for a in range(self.cnt(A)):
+            for j in range(self.n[B]):
+                o = off[j] + a * self.cmax[B] * nx
+                send[o:o + nx] = work[a, j]
         return send
 
-    def emulate_unpack_chunked(self, A, recv, nchunk):
-        """flat receive buffer (chunked layout) -> [cnt(B)][n[A]][nx]"""
+    def emulate_unpack_t(self, A, recv):
+        """flat receive buffer (blocks [a][b][x]) -> [cnt(B)][n[A]][nx]"""
         B, nx = 3 - A, self.n[0]
-        cc = self.chunking(A, nchunk)[0]
         out = np.zeros((self.cnt(B), self.n[A], nx))
-        off = self.unpack_offsets_chunk(A, nchunk)
+        off = self.unpack_offsets_t(A)
         for b in range(self.cnt(B)):
             for k in range(self.n[A]):
-                o = off[k] + b * cc * nx
+                o = off[k] + b * nx
                 out[b, k] = recv[o:o + nx]
         return out
 
@@ -262,10 +250,12 @@ class ShardedHeat3d:
             want = int(os.environ.get("ADSB_SHARDED_CHUNKS", "2" if mode == "ce" else "1"))
             min_planes = max(int(os.environ.get("ADSB_SHARDED_MIN_PLANES", "32")), max(p, 1))
             self.nchunk = max(1, min(want, min(self.plan.sizes[1] + self.plan.sizes[2]) // min_planes))
-        # doubles per (src, dst) block: the chunked layout of the copy-engine exchange pads differently
-        self.blk = self.plan.block
-        if mode == "ce":
-            self.blk = max(self.plan.chunking(A, self.nchunk)[2] for A in (1, 2))
+        self.blk = self.plan.block   # doubles per (src, dst) block
+        # copy-engine path: cumulative plane fractions at which the slab is cut.  Only the LAST chunk's
+        # exchange is exposed, so it is the small one; the first must still finish its exchange behind the
+        # last one's compute (measured: exchange ~0.4-0.7 x the compute of the same planes)
+        first = float(os.environ.get("ADSB_SHARDED_SPLIT", "0.62"))
+        self.fractions = [first * (i + 1) / (self.nchunk - 1) for i in range(self.nchunk - 1)] if self.nchunk > 1 else []
         if world > 1 and mode in ("p2p", "ce"):
             self._setup_p2p()
             if self.exchange == "p2p" and mode == "ce":
@@ -277,23 +267,16 @@ class ShardedHeat3d:
         if self.exchange in ("nccl", "ce"):
             self.send = torch.zeros(world * self.blk, **f64)
         if self.exchange == "ce":
-            # B sweep of chunk ci: other ranks' rows into the send blocks, my own rows into my receive block k
+            # B sweep: other ranks' rows into the send blocks, my own rows straight into my receive block k
             self._ce_off, self._ce_unpack = {}, {}
             for A in (1, 2):
-                B, nx = 3 - A, self.n[0]
-                cc, piece, _ = self.plan.chunking(A, self.nchunk)
-                blkA = self.plan.chunking(A, self.nchunk)[2]
-                u = self.plan.unpack_offsets_chunk(A, self.nchunk)
-                self._ce_unpack_blk = getattr(self, "_ce_unpack_blk", {})
-                self._ce_unpack_blk[A] = (u // blkA) * self.blk + u % blkA
+                B = 3 - A
+                self._ce_unpack[A] = self.plan.unpack_offsets_t(A)
                 for k in (0, 1):
-                    delta = (self.recv2[k].data_ptr() - self.send.data_ptr()) // 8
-                    for ci in range(len(self.plan.chunks_of(A, self.nchunk))):
-                        off = self.plan.pack_offsets_chunk(A, self.nchunk, ci)
-                        off = (off // self.plan.chunking(A, self.nchunk)[2]) * self.blk + off % self.plan.chunking(A, self.nchunk)[2]
-                        j0, jn = self.plan.starts[B][rank], self.plan.sizes[B][rank]
-                        off[j0:j0 + jn] += delta
-                        self._ce_off[A, k, ci] = off
+                    off = self.plan.pack_offsets_t(A)
+                    j0, jn = self.plan.starts[B][rank], self.plan.sizes[B][rank]
+                    off[j0:j0 + jn] += (self.recv2[k].data_ptr() - self.send.data_ptr()) // 8
+                    self._ce_off[A, k] = off
         self.step_index = 0
         self.timing, self._marks = False, []
         self.graph, self._eager_steps, self._graph_delta = None, 0, (0, 0)
@@ -517,8 +500,10 @@ class ShardedHeat3d:
         blk = self.blk
         main = torch.cuda.current_stream(self.dev)
         if ce:
-            chunks = plan.chunks_of(A, self.nchunk)
-            cc, piece, _ = plan.chunking(A, self.nchunk)
+            chunks = plan.chunks_of(A, self.fractions)
+            arow = plan.cmax[B] * nx          # doubles per A-plane of a block
+            s_send = [1, 0, 0]
+            s_send[A] = arow
         else:
             chunks = [(cs, cn) for cs, cn in zip(*split(c, self.nchunk)) if cn > 0]
         for ci, (cs, cn) in enumerate(chunks):
@@ -539,19 +524,19 @@ class ShardedHeat3d:
             self._mark("sweep_x")
             if ce:
                 # B sweep into the send blocks (own rows: my receive block); then the copy engines push this
-                # chunk's piece of every block -- contiguous: cnt_B(dst) rows of cc*nx doubles -- to the peers
-                self.ctx.sweep_view(B, 0, wk_ptr, _view(nout, v["work"][1]), self.send.data_ptr(),
-                                    _view(nout, v["send"][1]), off_out=self._ce_off[A, k, ci])
+                # chunk's piece of every block -- contiguous: cn planes of cmax[B]*nx doubles -- to the peers
+                self.ctx.sweep_view(B, 0, wk_ptr, _view(nout, v["work"][1]), self.send.data_ptr() + 8 * cs * arow,
+                                    _view(nout, s_send), off_out=self._ce_off[A, k])
                 self._mark("sweep_b")
                 self._chunk_events[ci].record(main)
                 for cs_ in self.copy_streams:
                     cs_.wait_event(self._chunk_events[ci])
                 for step_to in range(1, self.world):
                     dst = (self.rank + step_to) % self.world
-                    nbytes = 8 * plan.sizes[B][dst] * cc * nx
+                    nbytes = 8 * cn * arow
                     self.ctx_bg.set_stream(self.copy_streams[step_to % len(self.copy_streams)].cuda_stream)
-                    self.ctx_bg.copy2d(self.peers[dst] + 8 * (self.recv2_off[k] + self.rank * blk + ci * piece), nbytes,
-                                       self.send.data_ptr() + 8 * (dst * blk + ci * piece), nbytes, nbytes, 1)
+                    self.ctx_bg.copy2d(self.peers[dst] + 8 * (self.recv2_off[k] + self.rank * blk + cs * arow), nbytes,
+                                       self.send.data_ptr() + 8 * (dst * blk + cs * arow), nbytes, nbytes, 1)
                 continue
             self._chunk_events[ci].record(main)
             self.bg_stream.wait_event(self._chunk_events[ci])
@@ -573,9 +558,9 @@ class ShardedHeat3d:
         out_ptr = Hn.data_ptr() + 8 * p * plan.plane(B)
         if ce:
             s_recv = list(v["recv"][1])
-            s_recv[B] = cc * nx
+            s_recv[B] = nx
             self.ctx.sweep_view(A, 0, recv.data_ptr(), _view(v["recv"][0], s_recv), out_ptr, _view(*v["new"]),
-                                off_in=self._ce_unpack_blk[A])
+                                off_in=self._ce_unpack[A])
         else:
             self.ctx.sweep_view(A, 0, recv.data_ptr(), _view(*v["recv"]), out_ptr, _view(*v["new"]),
                                 off_in=self._off[A][1])

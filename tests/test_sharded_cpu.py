@@ -59,15 +59,13 @@ def _worker(rank, world, port, n, p, q):
         send = torch.from_numpy(plan.emulate_pack(1, got))
         back = plan.emulate_unpack(1, _all_to_all(send, plan, rank, world).numpy())  # [z_local][y][x]
         ok2 = np.array_equal(back, full[z0:z0 + cz])
-        # the chunked block layout of the copy-engine exchange (one contiguous piece per chunk and peer)
-        for nchunk in (2, 3):
-            blk = plan.chunking(2, nchunk)[2]
-            send = torch.from_numpy(plan.emulate_pack_chunked(2, full[z0:z0 + cz], nchunk))
-            everything = [torch.zeros_like(send) for _ in range(world)]
-            dist.all_gather(everything, send)
-            recv = torch.cat([everything[r][rank * blk:(rank + 1) * blk] for r in range(world)])
-            got = plan.emulate_unpack_chunked(2, recv.numpy(), nchunk)
-            ok1 = ok1 and np.array_equal(got, want)
+        # the block layout of the copy-engine exchange ([a][b][x]: any range of planes is one piece per peer)
+        send = torch.from_numpy(plan.emulate_pack_t(2, full[z0:z0 + cz]))
+        got = plan.emulate_unpack_t(2, _all_to_all(send, plan, rank, world).numpy())
+        ok1 = ok1 and np.array_equal(got, want)
+        for fr in ([0.62], [0.3, 0.6]):
+            ch = plan.chunks_of(2, fr)
+            ok1 = ok1 and sum(c for _, c in ch) == cz and ch[0][0] == 0 and all(c > 0 for _, c in ch)
         q.put((rank, ok1, ok2))
     finally:
         dist.destroy_process_group()
