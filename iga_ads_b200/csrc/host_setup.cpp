@@ -19,6 +19,7 @@
 
 #include "adsb200.h"
 #include "internal.hpp"
+#include "kernels.cuh"
 
 namespace adsb {
 
@@ -321,7 +322,7 @@ int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const in
     const int SC = ST * group;                                // chunks per line (some may be empty)
     const size_t rows = static_cast<size_t>(SC) * ch + KL + KD;
     P.n = n; P.KL = KL; P.KD = KD; P.piv = piv ? 1 : 0; P.CH = ch; P.R = group; P.SC = SC; P.ST = ST;
-    P.LF = KL + (KL & 1); P.LB = (KD + 1) + ((KD + 1) & 1); P.LC = (KD + KL) + ((KD + KL) & 1);
+    P.LF = sweep_pitch(KL); P.LB = sweep_pitch(KD + 1); P.LC = sweep_pitch(KD + KL);
     P.rows = static_cast<int>(rows);
     std::vector<double> Lm(rows * KL, 0.0), Ut(rows * KD, 0.0), rinv(rows, 0.0), Phi(rows * KL, 0.0),
         Psi(rows * KD, 0.0), Xi(rows * KL, 0.0), T(static_cast<size_t>(SC) * KL * KL, 0.0),

@@ -83,7 +83,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
 
 template <int P, int NPT, int NWARP, int NSTAGE, int MINB, bool FORCING, int XP>
 __global__ void __launch_bounds__(NWARP * 32, MINB)
-    rhs_tma_kernel(const __grid_constant__ CUtensorMap tmap, const RhsOps ops, const RhsGeom g, int zseg) {
+    rhs_tma_kernel(const __grid_constant__ CUtensorMap tmap, const RhsOps ops, const RhsGeom g, int zseg, int zfirst) {
     using C = Cfg<P, NPT, NWARP, NSTAGE, XP>;
     constexpr int W = C::W, PH = C::PH, TY = C::TY, UH = C::UH, RW = C::RW, NTH = C::NTH, TXV = C::TXV;
     constexpr uint32_t RAWS = C::RAW_STRIDE, PQB = C::PQ_BYTES;
@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
     const int x0 = g.out_lo[0] + blockIdx.x * TXV;
     const int y0 = g.out_lo[1] + blockIdx.y * TY;
     const int nx = ops.n[0], ny = ops.n[1];
-    const int zs = g.out_lo[2] + blockIdx.z * zseg;
-    const int ze = min(zs + zseg, g.out_lo[2] + g.out_n[2]);
+    // z segments: the first one has zfirst planes, the others zseg (see launch_cfg)
+    const int zs = g.out_lo[2] + (blockIdx.z == 0 ? 0 : zfirst + ((int) blockIdx.z - 1) * zseg);
+    const int ze = blockIdx.z == 0 ? g.out_lo[2] + min(zfirst, g.out_n[2]) : min(zs + zseg, g.out_lo[2] + g.out_n[2]);
     const int kb = zs - P;
     const int NP = ze - zs + 2 * P;  // input planes kb .. kb + NP - 1
 
@@ -384,12 +385,29 @@ int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
         }
     }
     if (best < 0) return -1;
-    const int nseg = (g.out_n[2] + zseg - 1) / zseg;
-    const int smem = C::FIXED_BYTES + (zseg + 2 * P) * C::W * 16;
+    int zfirst = zseg;
+    int nseg = (g.out_n[2] + zseg - 1) / zseg;
+    // One column cannot fill the device twice over (tiles < slots < 2 tiles): cut every column into a LONG
+    // and a SHORT segment.  CTAs are dispatched in block order, so the `tiles` long segments start first
+    // and the slots left over work through the short ones, j = ceil(tiles / spare) in a row each, while
+    // the long ones run; lengths chosen so both finish together:  long + c = j (short + c).
+    if (tiles < slots && slots < 2 * tiles) {
+        const long long spare = slots - tiles;
+        const long long j = (tiles + spare - 1) / spare;
+        const int c = 2 * P + 4;
+        const int zshort = (int) ((g.out_n[2] + c - c * j) / (j + 1));
+        const int zlong = g.out_n[2] - zshort;
+        if (zshort >= 8 * P && zlong <= zcap && (long long) (zlong + c) < best) {
+            zfirst = zlong;
+            zseg = zshort;
+            nseg = 2;
+        }
+    }
+    const int smem = C::FIXED_BYTES + ((zfirst > zseg ? zfirst : zseg) + 2 * P) * C::W * 16;
     cudaError_t e = cudaFuncSetAttribute((const void*) kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int) e;
     dim3 grid(tx, ty, nseg), block(C::NTH, 1, 1);
-    kern<<<grid, block, smem, st>>>(map, ops, g, zseg);
+    kern<<<grid, block, smem, st>>>(map, ops, g, zseg, zfirst);
     return (int) cudaGetLastError();
 }
 

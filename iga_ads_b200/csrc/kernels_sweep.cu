@@ -39,7 +39,7 @@ namespace {
 template <int KL, int KD, bool PIV, int CH, int RL, bool CONTIG>
 __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepFactor F, const SweepGeom G) {
     extern __shared__ __align__(16) double smem[];
-    constexpr int LF = KL + (KL & 1), LB = (KD + 1) + ((KD + 1) & 1), LC = (KD + KL) + ((KD + KL) & 1);
+    constexpr int LF = sweep_pitch(KL), LB = sweep_pitch(KD + 1), LC = sweep_pitch(KD + KL);
     constexpr int MD = SWEEP_MAX_DEPTH_DEV;
     const int NLt = blockDim.x, SC = blockDim.y, NL = NLt * RL;
     const int tx = threadIdx.x, c = threadIdx.y;  // c: chunk of this thread

@@ -50,7 +50,7 @@ template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
 __global__ void __launch_bounds__(288, 1)
     sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G) {
     constexpr int RL = SWEEP_RL, NLt = NL / RL;
-    constexpr int LF = KL + (KL & 1), LB = (KD + 1) + ((KD + 1) & 1), LC = (KD + KL) + ((KD + KL) & 1);
+    constexpr int LF = sweep_pitch(KL), LB = sweep_pitch(KD + 1), LC = sweep_pitch(KD + KL);
     constexpr int MD = SWEEP_MAX_DEPTH_DEV;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int SC = F0.SC;
@@ -397,7 +397,7 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
         T.maps = it->second;
     }
     T.tile_doubles = (T.tile_doubles + 15) & ~15;  // 128 B granules
-    const int LF = F.KL + (F.KL & 1), LB = (F.KD + 1) + ((F.KD + 1) & 1), LC = (F.KD + F.KL) + ((F.KD + F.KL) & 1);
+    const int LF = sweep_pitch(F.KL), LB = sweep_pitch(F.KD + 1), LC = sweep_pitch(F.KD + F.KL);
     const int rows = F.SC * SWEEP_CH + F.KL + F.KD;
     const size_t fixed_doubles = (size_t) F.SC * (F.KL + F.KD) * NL + (size_t) rows * (LF + LB + LC) +
                                  (size_t) F.SC * (F.KL * F.KL + F.KD * F.KD) * SWEEP_MAX_DEPTH_DEV;

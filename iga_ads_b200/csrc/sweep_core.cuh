@@ -41,7 +41,8 @@ __device__ __forceinline__ void sweep_sync(int nsync) {
 template <int KL, int KD, bool PIV, int CH, int RL, bool CS = false>
 __device__ __forceinline__ void sweep_core(const SweepFactor& F, double (&v)[RL][CH + KL], double* fst, double* bst,
                                            int c, int tx, int NLt, int SC, int nsync = 0) {
-    constexpr int LF = KL + (KL & 1), LB = (KD + 1) + ((KD + 1) & 1), LC = (KD + KL) + ((KD + KL) & 1);
+    constexpr int LF = sweep_pitch(KL), LB = sweep_pitch(KD + 1), LC = sweep_pitch(KD + KL);
+    constexpr int RF = sweep_rec(KL), RB = sweep_rec(KD + 1), RC = sweep_rec(KD + KL);  // doubles loaded per record
     constexpr int MD = SWEEP_MAX_DEPTH_DEV;
     const int NL = NLt * RL;
     const int j0 = c * CH;
@@ -56,8 +57,8 @@ __device__ __forceinline__ void sweep_core(const SweepFactor& F, double (&v)[RL]
         const int* pv = F.pv + j0;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-            double L[LF];
-            ldrec<LF, CS>(cf + i * LF, L);
+            double L[RF];
+            ldrec<RF, CS>(cf + i * LF, L);
             int t = 0;
             if (PIV) t = __ldg(pv + i);
 #pragma unroll
@@ -90,8 +91,8 @@ __device__ __forceinline__ void sweep_core(const SweepFactor& F, double (&v)[RL]
         const double* cf = F.cfB + (long long) j0 * LB;
 #pragma unroll
         for (int i = CH - 1; i >= 0; --i) {
-            double Ub[LB];
-            ldrec<LB, CS>(cf + i * LB, Ub);
+            double Ub[RB];
+            ldrec<RB, CS>(cf + i * LB, Ub);
 #pragma unroll
             for (int r = 0; r < RL; ++r) {
                 double acc = v[r][i];
@@ -235,8 +236,8 @@ __device__ __forceinline__ void sweep_core(const SweepFactor& F, double (&v)[RL]
         const double* cf = F.cfC + (long long) j0 * LC;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-            double C[LC];
-            ldrec<LC, CS>(cf + i * LC, C);
+            double C[RC];
+            ldrec<RC, CS>(cf + i * LC, C);
 #pragma unroll
             for (int r = 0; r < RL; ++r) {
                 double acc = v[r][i];
