@@ -87,6 +87,7 @@ _SIGNATURES = {
     "adsb_zero": (c_int, [vp, c_int]),
     "adsb_bind": (c_int, [vp, c_int, vp]),
     "adsb_device_ptr": (vp, [vp, c_int]),
+    "adsb_row_pitch": (c_ll, [vp]),
     "adsb_set_plane": (c_int, [vp, c_int, c_int, c_int, dp]),
     "adsb_compute_rhs": (c_int, [vp, ctypes.POINTER(Form), c_int, c_int]),
     "adsb_load_tensor": (c_int, [vp, c_int, c_int, c_int]),

@@ -61,7 +61,12 @@ struct adsb_ctx {
     long long launches = 0;
     int sm_limit = 0;  // adsb_set_sm_limit
     RhsSide side;      // second stream + events for the x-remainder kernel of the right-hand side (lazy)
-    size_t local_size() const { return (size_t) cnt[0] * cnt[1] * cnt[2]; }
+    // Managed tensors keep the reference's index order (x fastest) but pad every x row to an EVEN number of
+    // doubles: rows, planes and the tensor itself then start 16 B aligned, which is what the TMA-fed
+    // kernels need (n = elements + p is odd for every odd degree).  The pad column is never read as data.
+    long long pitch0() const { return cnt[0] + (cnt[0] & 1); }
+    size_t local_size() const { return (size_t) pitch0() * cnt[1] * cnt[2]; }   // doubles allocated
+    size_t rows() const { return (size_t) cnt[1] * cnt[2]; }
 };
 
 namespace {
@@ -100,6 +105,7 @@ int ensure_buf(adsb_ctx* c, int b) {
     if (b < 0 || b >= ADSB_MAX_BUFFERS) return fail(ADSB_EINVAL, "buffer id out of range");
     if (!c->buf[b]) {
         CU(cudaMalloc((void**) &c->buf[b], c->local_size() * sizeof(double)));
+        CU(cudaMemsetAsync(c->buf[b], 0, c->local_size() * sizeof(double), c->stream));  // finite pad column
         c->owned[b] = true;
     }
     return ADSB_OK;
@@ -244,8 +250,8 @@ adsb_view local_view(const adsb_ctx* c) {
     adsb_view v{};
     for (int d = 0; d < 3; ++d) v.n[d] = c->cnt[d];
     v.s[0] = 1;
-    v.s[1] = c->cnt[0];
-    v.s[2] = (long long) c->cnt[0] * c->cnt[1];
+    v.s[1] = c->pitch0();
+    v.s[2] = c->pitch0() * c->cnt[1];
     return v;
 }
 
@@ -571,7 +577,8 @@ int adsb_upload(adsb_ctx* c, int b, const double* host) {
     if (!c || !host) return fail(ADSB_EINVAL, "upload: null argument");
     if (int rc = select_device(c)) return rc;
     if (int rc = ensure_buf(c, b)) return rc;
-    CU(cudaMemcpyAsync(c->buf[b], host, c->local_size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->buf[b], c->pitch0() * sizeof(double), host, c->cnt[0] * sizeof(double),
+                         c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return ADSB_OK;
 }
@@ -580,7 +587,8 @@ int adsb_download(adsb_ctx* c, int b, double* host) {
     if (!c || !host) return fail(ADSB_EINVAL, "download: null argument");
     if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "download: buffer not allocated");
     if (int rc = select_device(c)) return rc;
-    CU(cudaMemcpyAsync(host, c->buf[b], c->local_size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(host, c->cnt[0] * sizeof(double), c->buf[b], c->pitch0() * sizeof(double),
+                         c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return ADSB_OK;
 }
@@ -609,6 +617,8 @@ int adsb_bind(adsb_ctx* c, int b, double* p) {
     return ADSB_OK;
 }
 
+long long adsb_row_pitch(adsb_ctx* c) { return c ? c->pitch0() : 0; }
+
 double* adsb_device_ptr(adsb_ctx* c, int b) {
     if (!c || b < 0 || b >= ADSB_MAX_BUFFERS) return nullptr;
     if (select_device(c) || ensure_buf(c, b)) return nullptr;
@@ -621,7 +631,7 @@ int adsb_set_plane(adsb_ctx* c, int b, int axis, int idx, const double* values) 
     if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "set_plane: buffer not allocated");
     if (int rc = select_device(c)) return rc;
     adsb_view v = local_view(c);
-    size_t count = c->local_size() / c->cnt[axis];
+    size_t count = (size_t) c->cnt[0] * c->cnt[1] * c->cnt[2] / c->cnt[axis];
     double* d = nullptr;
     CU(cudaMalloc((void**) &d, count * sizeof(double)));
     CU(cudaMemcpyAsync(d, values, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -739,7 +749,7 @@ int adsb_load_tensor(adsb_ctx* c, int source, int with_test_function, int dst) {
     if (int rc = quad_axes(c, A)) return rc;
     StageTimer t(c, 4);
     if (with_test_function) {
-        cudaError_t e = (cudaError_t) launch_project(3, A, c->buf[dst], c->lo, c->cnt, c->stream);
+        cudaError_t e = (cudaError_t) launch_project(3, A, c->buf[dst], c->lo, c->cnt, c->stream, c->pitch0());
         if (e != cudaSuccess) return cuda_fail(e, "project kernel");
         c->launches++;
         return ADSB_OK;
@@ -755,7 +765,8 @@ int adsb_load_tensor(adsb_ctx* c, int source, int with_test_function, int dst) {
     double* G = nullptr;
     CU(cudaMalloc((void**) &G, count * sizeof(double)));
     cudaError_t e = (cudaError_t) launch_element_source(3, A, G, elo, en, c->stream);
-    if (e == cudaSuccess) e = (cudaError_t) launch_box_sum(A, G, c->buf[dst], elo, en, c->lo, c->cnt, c->stream);
+    if (e == cudaSuccess)
+        e = (cudaError_t) launch_box_sum(A, G, c->buf[dst], elo, en, c->lo, c->cnt, c->stream, c->pitch0());
     c->launches += 2;
     cudaError_t e2 = cudaStreamSynchronize(c->stream);
     cudaFree(G);
@@ -772,7 +783,7 @@ int adsb_project_init(adsb_ctx* c, int state, int dst) {
     QuadAxes A;
     if (int rc = quad_axes(c, A)) return rc;
     StageTimer t(c, 4);
-    cudaError_t e = (cudaError_t) launch_project(state, A, c->buf[dst], c->lo, c->cnt, c->stream);
+    cudaError_t e = (cudaError_t) launch_project(state, A, c->buf[dst], c->lo, c->cnt, c->stream, c->pitch0());
     if (e != cudaSuccess) return cuda_fail(e, "project kernel");
     c->launches++;
     return ADSB_OK;

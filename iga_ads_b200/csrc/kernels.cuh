@@ -126,10 +126,12 @@ struct QuadAxes {
     const double* w[3];   // [q]
     const double* J[3];   // [ne]
 };
-int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], const int n[3], cudaStream_t st);
+// pitch0: doubles between consecutive x rows of `out` (0: dense, n[0])
+int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], const int n[3], cudaStream_t st,
+                   long long pitch0 = 0);
 int launch_element_source(int src, const QuadAxes& A, double* G, const int elo[3], const int en[3], cudaStream_t st);
 int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int elo[3], const int en[3],
-                   const int lo[3], const int n[3], cudaStream_t st);
+                   const int lo[3], const int n[3], cudaStream_t st, long long pitch0 = 0);
 
 // General quadrature right-hand side (kernels_quadrhs.cu): elements [elo, elo+en) are integrated and
 // scattered (atomically) into the DOFs of g's out box, which must be zero on entry.  source: built-in

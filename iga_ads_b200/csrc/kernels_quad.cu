@@ -46,7 +46,8 @@ __device__ __forceinline__ double source(double x, double y, double z, bool d3) 
 }
 
 template <int SRC>
-__global__ void project_kernel(const QuadAxes A, double* out, int lo0, int lo1, int lo2, int n0, int n1, int n2) {
+__global__ void project_kernel(const QuadAxes A, double* out, int lo0, int lo1, int lo2, int n0, int n1, int n2,
+                               long long pitch0) {
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i1 = blockIdx.y, i2 = blockIdx.z;
     if (i0 >= n0) return;
@@ -76,7 +77,7 @@ __global__ void project_kernel(const QuadAxes A, double* out, int lo0, int lo1, 
                             acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(__dmul_rn(f, B), w), J));
                         }
             }
-    out[i0 + (long long) n0 * (i1 + (long long) n1 * i2)] = acc;
+    out[i0 + pitch0 * (i1 + (long long) n1 * i2)] = acc;
 }
 
 // G[e] = sum_q f(x_q) w J over the element box [elo, elo+en)
@@ -103,7 +104,7 @@ __global__ void element_source_kernel(const QuadAxes A, double* G, int elo0, int
 }
 
 __global__ void box_sum_kernel(const QuadAxes A, const double* G, double* out, int elo0, int elo1, int elo2, int en0,
-                               int en1, int lo0, int lo1, int lo2, int n0, int n1, int n2) {
+                               int en1, int lo0, int lo1, int lo2, int n0, int n1, int n2, long long pitch0) {
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i1 = blockIdx.y, i2 = blockIdx.z;
     if (i0 >= n0) return;
@@ -115,18 +116,20 @@ __global__ void box_sum_kernel(const QuadAxes A, const double* G, double* out, i
         for (int e1 = max(a1 - p1, 0); e1 <= min(a1, A.ne[1] - 1); ++e1)
             for (int e2 = d3 ? max(a2 - p2, 0) : 0; e2 <= (d3 ? min(a2, A.ne[2] - 1) : 0); ++e2)
                 acc += G[(e0 - elo0) + (long long) en0 * ((e1 - elo1) + (long long) en1 * (e2 - elo2))];
-    out[i0 + (long long) n0 * (i1 + (long long) n1 * i2)] = acc;
+    out[i0 + pitch0 * (i1 + (long long) n1 * i2)] = acc;
 }
 
 }  // namespace
 
-int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], const int n[3], cudaStream_t st) {
+int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], const int n[3], cudaStream_t st,
+                   long long pitch0) {
+    if (pitch0 <= 0) pitch0 = n[0];
     dim3 block(128, 1, 1), grid((n[0] + 127) / 128, n[1], n[2]);
     switch (src) {
-    case 0: project_kernel<0><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2]); break;
-    case 1: project_kernel<1><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2]); break;
-    case 2: project_kernel<2><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2]); break;
-    case 3: project_kernel<3><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2]); break;
+    case 0: project_kernel<0><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2], pitch0); break;
+    case 1: project_kernel<1><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2], pitch0); break;
+    case 2: project_kernel<2><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2], pitch0); break;
+    case 3: project_kernel<3><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2], pitch0); break;
     default: return (int) cudaErrorInvalidValue;
     }
     return (int) cudaGetLastError();
@@ -145,10 +148,11 @@ int launch_element_source(int src, const QuadAxes& A, double* G, const int elo[3
 }
 
 int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int elo[3], const int en[3],
-                   const int lo[3], const int n[3], cudaStream_t st) {
+                   const int lo[3], const int n[3], cudaStream_t st, long long pitch0) {
+    if (pitch0 <= 0) pitch0 = n[0];
     dim3 block(128, 1, 1), grid((n[0] + 127) / 128, n[1], n[2]);
     box_sum_kernel<<<grid, block, 0, st>>>(A, G, out, elo[0], elo[1], elo[2], en[0], en[1], lo[0], lo[1], lo[2], n[0],
-                                           n[1], n[2]);
+                                           n[1], n[2], pitch0);
     return (int) cudaGetLastError();
 }
 

@@ -421,7 +421,10 @@ int launch_rhs_tma(const RhsOps& ops, const RhsGeom& g, cudaStream_t st, bool na
     auto even = [](long long v) { return (v & 1) == 0; };
     if (g.si[0] != 1 || g.so[0] != 1) return -1;
     // TMA: 16 B aligned base and strides; pair stores: even output extents / strides
-    if (!even(g.si[1]) || !even(g.si[2]) || !even(g.so[1]) || !even(g.so[2]) || !even(g.out_n[0])) return -1;
+    if (!even(g.si[1]) || !even(g.si[2]) || !even(g.so[1]) || !even(g.so[2])) return -1;
+    // an odd row length is fine when the last pair's second element is a pad column: the box ends at the
+    // domain edge and the output rows are pitched wider than the box (the managed tensors' layout)
+    if (!even(g.out_n[0]) && !(g.out_lo[0] + g.out_n[0] == ops.n[0] && g.so[1] > g.out_n[0])) return -1;
     if ((uintptr_t) g.in % 16 || (uintptr_t) g.out % 16 || (g.forcing && (uintptr_t) g.forcing % 16)) return -1;
     for (int d = 0; d < 3; ++d)  // outside `in` reads as zero: only right when `in` does not stick out of the domain
         if (g.in_lo[d] < 0 || g.in_lo[d] + g.in_n[d] > ops.n[d]) return -1;

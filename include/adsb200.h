@@ -125,6 +125,11 @@ int adsb_swap(adsb_ctx* ctx, int buf_a, int buf_b);        /* std::swap(u, u_pre
 int adsb_zero(adsb_ctx* ctx, int buf);                      /* zero(rhs), tensor.hpp:44-50 */
 int adsb_bind(adsb_ctx* ctx, int buf, double* device_ptr);  /* adopt caller-owned device memory */
 double* adsb_device_ptr(adsb_ctx* ctx, int buf);
+/* Device layout of the managed tensors: the reference's index order (x fastest) with every x row padded to
+ * adsb_row_pitch() doubles (cnt[0] rounded up to even, so rows are 16 B aligned for the TMA-fed kernels);
+ * element (i, j, k) sits at i + pitch * (j + cnt[1] * k).  adsb_upload / adsb_download convert from / to the
+ * dense host layout; memory handed to adsb_bind must follow the padded layout. */
+long long adsb_row_pitch(adsb_ctx* ctx);
 
 /* Overwrite the hyper-plane index `idx` of `axis` with `values` (host, product of the other
  * extents doubles).  Replaces the Dirichlet overwrite `v(0,i) = buf(i)` of
