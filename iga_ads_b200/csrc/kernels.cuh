@@ -10,16 +10,10 @@ constexpr int SWEEP_CH = 18;  // columns per chunk (one chunk per thread, held i
 constexpr int SWEEP_RL = 2;   // lines per thread: they share every coefficient load and interleave for ILP
 constexpr int SWEEP_MAX_DEPTH_DEV = 6;
 // Coefficient records (multipliers, U rows, Psi|Xi) of one column: `sweep_rec` doubles are loaded (even: 128-bit
-// loads), records are `sweep_pitch` doubles apart.  The lanes of a warp read the records of 4 chunks, CH
-// columns apart: the pitch is chosen so that those 4 records never fall on the same shared-memory banks
-// (CH * pitch * 8 bytes must not be a multiple of 64 -- with pitch 4 every other chunk collided: 30 % of the
-// sweep kernels' shared-memory wavefronts were conflict replays, profiles/r1b_ncu_step_kernels.txt).
+// loads), records are `sweep_pitch` doubles apart.  (A wider pitch that keeps the 4 chunks a warp touches off
+// each other's banks was measured: no gain, and its 17 KB of shared memory cost a ring slot.)
 __host__ __device__ constexpr int sweep_rec(int len) { return len + (len & 1); }
-__host__ __device__ constexpr int sweep_pitch(int len) {
-    int p = sweep_rec(len);
-    while ((SWEEP_CH * p * 8) % 64 == 0) p += 2;
-    return p;
-}
+__host__ __device__ constexpr int sweep_pitch(int len) { return sweep_rec(len); }
 constexpr int SWEEP_MAX_BOXES = 32;      // TMA boxes per tile and direction (tile-streaming sweep kernel)  // == SWEEP_MAX_DEPTH of internal.hpp
 
 // One factorised band matrix, prepared by build_sweep_plan (host_setup.cpp).
