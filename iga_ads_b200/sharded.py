@@ -287,7 +287,8 @@ class ShardedHeat3d:
             self.sm_count = torch.cuda.get_device_properties(self.dev).multi_processor_count
             self.bg_stream = torch.cuda.Stream(device=self.dev)
             # peer copies to different destinations go round-robin over a few streams (several copy engines)
-            self.copy_streams = [self.bg_stream] + [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+            ncs = max(1, int(os.environ.get("ADSB_SHARDED_COPY_STREAMS", "3")))
+            self.copy_streams = [self.bg_stream] + [torch.cuda.Stream(device=self.dev) for _ in range(ncs - 1)]
             self.ctx_bg = Context(self.n, device=device)   # same tables and factors, its own stream
             self.ctx_bg.set_stream(self.bg_stream.cuda_stream)
             for ax in range(3):

@@ -308,3 +308,63 @@ def test_sharded_two_ranks_vs_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(root, "tests", "sharded_check.py")], capture_output=True, text=True, timeout=600)
     assert "SHARDED_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------- thin slabs (8-GPU shards of small problems)
+@pytest.mark.parametrize("p,ne,planes", [(2, 30, 4), (2, 30, 8), (3, 21, 3), (2, 30, 16)])
+def test_thin_slab_views_match_whole_tensor(p, ne, planes):
+    """The pointer-level entry points on a slab of a few planes (what a rank of an 8-GPU run owns) must
+    reproduce the whole-tensor kernels: right-hand side of planes [z0, z0+planes) from a halo'ed input
+    box, and the x / y sweeps restricted to those planes."""
+    import torch
+
+    from iga_ads_b200._lib import View
+
+    n, dt = ne + p, 1e-7
+    sim = make_problem("heat_3d", p, ne, dt)
+    ctx = sim.ctx
+    u0 = synthetic_state((n, n, n))
+    ctx.upload(U_PREV, u0)
+    form = Form.make(1.0, (dt, dt, dt))
+    ctx.compute_rhs(form, U_PREV, U)
+    rhs_full = ctx.download(U).reshape(n, n, n)
+    ctx.sweep(U, 0)
+    x_full = ctx.download(U).reshape(n, n, n)
+    ctx.sweep(U, 1)
+    xy_full = ctx.download(U).reshape(n, n, n)
+
+    dev = torch.device("cuda", 0)
+    for z0 in (0, planes, n - planes):
+        lo, hi = max(0, z0 - p), min(n, z0 + planes + p)
+        src = torch.from_numpy(u0.reshape(n, n, n)[lo:hi].copy()).to(dev)
+        out = torch.zeros(planes * n * n, dtype=torch.float64, device=dev)
+        strides = [1, n, n * n]
+        ctx.rhs_view(form, src.data_ptr(), View.make([n, n, hi - lo], strides), [0, 0, lo], out.data_ptr(),
+                     View.make([n, n, planes], strides), [0, 0, z0])
+        ctx.synchronize()
+        got = out.cpu().numpy().reshape(planes, n, n)
+        assert rel_l2(got.ravel(), rhs_full[z0:z0 + planes].ravel()) < 1e-13, ("rhs", z0)
+        v = View.make([n, n, planes], strides)
+        ctx.sweep_view(0, 0, out.data_ptr(), v, out.data_ptr(), v)
+        ctx.synchronize()
+        got = out.cpu().numpy().reshape(planes, n, n)
+        assert rel_l2(got.ravel(), x_full[z0:z0 + planes].ravel()) < 1e-12, ("sweep x", z0)
+        ctx.sweep_view(1, 0, out.data_ptr(), v, out.data_ptr(), v)
+        ctx.synchronize()
+        got = out.cpu().numpy().reshape(planes, n, n)
+        assert rel_l2(got.ravel(), xy_full[z0:z0 + planes].ravel()) < 1e-12, ("sweep y", z0)
+
+
+@pytest.mark.parametrize("world,p,ne", [(4, 2, 30), (8, 3, 21)])
+def test_virtual_ranks_emulate_the_sharded_step(world, p, ne):
+    """The slab-sharded step with `world` virtual ranks run one after the other on this GPU (same SlabPlan,
+    pointer-level kernels and multi-piece offset tables as a real multi-GPU run; the all-to-all is a block
+    shuffle): two steps (both slab orientations) against the oracle."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("virtual_ranks", os.path.join(root, "tools", "virtual_ranks.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(world, p, ne) < (1e-12 if p == 2 else 2e-12)
