@@ -174,7 +174,8 @@ int get_offsets(adsb_ctx* c, const long long* host, int n, const long long** dev
 
 // sweep along `axis` of a view; see adsb_sweep_view
 int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view& vi,
-               const long long* off_in_h, double* out, const adsb_view& vo, const long long* off_out_h) {
+               const long long* off_in_h, double* out, const adsb_view& vo, const long long* off_out_h,
+               bool managed = false) {
     if (axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "sweep: bad axis");
     if (slot < 0 || slot >= ADSB_MAX_SLOTS || !c->ax[axis].fac[slot].set)
         return fail(ADSB_ESTATE, "sweep: no factor uploaded for this axis/slot");
@@ -212,6 +213,8 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     G.s1_in = vi.s[l1];
     G.s1_out = vo.s[l1];
     G.max_ctas = c->sm_limit;
+    // managed tensors pad every x row: an in-place x sweep of an odd-length line may move the pad along
+    G.pad_ok = managed && in == out && axis == 0 && vi.s[1] > vi.n[0];
     G.pitch = F.n + (F.n & 1);
     if (G.pitch % 4 == 0) G.pitch += 2;  // pitch = 2 (mod 4): conflict-free 128-bit column access
     G.bulk = 0;
@@ -577,8 +580,11 @@ int adsb_upload(adsb_ctx* c, int b, const double* host) {
     if (!c || !host) return fail(ADSB_EINVAL, "upload: null argument");
     if (int rc = select_device(c)) return rc;
     if (int rc = ensure_buf(c, b)) return rc;
-    CU(cudaMemcpy2DAsync(c->buf[b], c->pitch0() * sizeof(double), host, c->cnt[0] * sizeof(double),
-                         c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyHostToDevice, c->stream));
+    if (c->pitch0() == c->cnt[0])
+        CU(cudaMemcpyAsync(c->buf[b], host, c->local_size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    else
+        CU(cudaMemcpy2DAsync(c->buf[b], c->pitch0() * sizeof(double), host, c->cnt[0] * sizeof(double),
+                             c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return ADSB_OK;
 }
@@ -587,8 +593,11 @@ int adsb_download(adsb_ctx* c, int b, double* host) {
     if (!c || !host) return fail(ADSB_EINVAL, "download: null argument");
     if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "download: buffer not allocated");
     if (int rc = select_device(c)) return rc;
-    CU(cudaMemcpy2DAsync(host, c->cnt[0] * sizeof(double), c->buf[b], c->pitch0() * sizeof(double),
-                         c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyDeviceToHost, c->stream));
+    if (c->pitch0() == c->cnt[0])
+        CU(cudaMemcpyAsync(host, c->buf[b], c->local_size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    else
+        CU(cudaMemcpy2DAsync(host, c->cnt[0] * sizeof(double), c->buf[b], c->pitch0() * sizeof(double),
+                             c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return ADSB_OK;
 }
@@ -682,7 +691,7 @@ int adsb_sweep(adsb_ctx* c, int b, int axis, int slot) {
     if (c->cnt[axis] != c->ng[axis]) return fail(ADSB_ESTATE, "sweep: this context does not own whole lines of the axis");
     if (int rc = select_device(c)) return rc;
     adsb_view v = local_view(c);
-    return sweep_impl(c, axis, slot, c->buf[b], v, nullptr, c->buf[b], v, nullptr);
+    return sweep_impl(c, axis, slot, c->buf[b], v, nullptr, c->buf[b], v, nullptr, true);
 }
 
 int adsb_solve(adsb_ctx* c, int b, const int* slots) {
@@ -703,7 +712,9 @@ int adsb_step(adsb_ctx* c, int u, int up, const adsb_substep* sub, int nsub, int
                 if (ax >= c->ndim || sub[s].fix_buf < 0 || sub[s].fix_buf >= ADSB_MAX_BUFFERS || !c->buf[sub[s].fix_buf])
                     return fail(ADSB_ESTATE, "step: bad fix_axis / fix_buf");
                 adsb_view v = local_view(c);
-                cudaError_t e = (cudaError_t) launch_set_plane(c->buf[u], v.s, v.n, ax, 0, c->buf[sub[s].fix_buf], c->stream);
+                // the plane values are the first elements (host order) of the managed tensor fix_buf
+                cudaError_t e = (cudaError_t) launch_set_plane(c->buf[u], v.s, v.n, ax, 0, c->buf[sub[s].fix_buf], c->stream,
+                                                               c->cnt[0], c->pitch0());
                 if (e != cudaSuccess) return cuda_fail(e, "set_plane kernel");
                 c->launches++;
             }

@@ -44,6 +44,8 @@ struct SweepGeom {
     int pitch;  // CONTIG: shared-memory row pitch in doubles (even)
     int bulk;   // CONTIG: rows are 16 B aligned on both sides -> TMA bulk copies
     int max_ctas;  // persistent kernels: at most this many CTAs (0: one per SM)
+    int pad_ok;    // CONTIG, odd n: every line is followed by a pad element inside the allocation (managed
+                   // tensors, in place): bulk copies may move n+1 doubles so that they stay 16 B multiples
 };
 
 // Tile-streaming variant (kernels_sweep_tile.cu): persistent CTAs, TMA-fed shared-memory ring.
@@ -54,6 +56,7 @@ struct SweepTileGeom {
     int L0, L1;        // lines: l0 in [0, L0) (x for the strided sweeps), l1 in [0, L1)
     int nb0, ntiles;   // tiles of 16 lines along l0; nb0 * L1 tiles in all
     int pitch;         // CONTIG: shared row pitch of a line (doubles)
+    int ncopy;         // CONTIG: doubles moved per line (n, or n+1 when n is odd and the line has a pad element)
     // STRIDED: a tile is moved as boxes of whole rows, one tensor map per box (exact extents, so a
     // box never spills over its neighbour): maps[0 .. nbox_in) load, maps[nbox_in .. +nbox_out) store
     const void* maps;  // CUtensorMap array in global memory
@@ -135,8 +138,9 @@ int launch_rhs_quadrature(int ndim, const QuadAxes& A, const RhsGeom& g, int sou
 int launch_zero_box(double* y, const int n[3], const long long s[3], cudaStream_t st);
 int launch_axpy_box(double* y, const double* x, double a, const int n[3], const long long s[3], cudaStream_t st);
 
+// vnx > 0: `values` are the first elements of a tensor with x rows of vnx doubles, vpitch apart (else dense)
 int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,
-                     const double* values, cudaStream_t st);
+                     const double* values, cudaStream_t st, int vnx = 0, long long vpitch = 0);
 
 }  // namespace adsb
 

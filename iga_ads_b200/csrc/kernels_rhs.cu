@@ -558,10 +558,16 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
     return rc;
 }
 
-__global__ void set_plane_kernel(double* t, long long sa, long long sb, int na, int nb, const double* values) {
+// values: dense plane [b][a], stored either densely (vnx huge) or as the first elements of a managed tensor
+// (dense index i sits at i % vnx + vpitch * (i / vnx): x rows of vnx doubles, vpitch apart)
+__global__ void set_plane_kernel(double* t, long long sa, long long sb, int na, int nb, const double* values, int vnx,
+                                 long long vpitch) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (a < na && b < nb) t[a * sa + b * sb] = values[a + (long long) b * na];
+    if (a < na && b < nb) {
+        const long long i = a + (long long) b * na;
+        t[a * sa + b * sb] = values[i % vnx + vpitch * (i / vnx)];
+    }
 }
 
 }  // namespace
@@ -593,11 +599,15 @@ int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& g, cudaStre
 }
 
 int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,
-                     const double* values, cudaStream_t st) {
+                     const double* values, cudaStream_t st, int vnx, long long vpitch) {
+    if (vnx <= 0) {  // dense values
+        vnx = 0x7fffffff;
+        vpitch = 0;
+    }
     int a = (axis + 1) % 3, b = (axis + 2) % 3;
     if (a > b) { int tmp = a; a = b; b = tmp; }
     dim3 block(128, 1, 1), grid((n[a] + 127) / 128, n[b], 1);
-    set_plane_kernel<<<grid, block, 0, st>>>(t + idx * s[axis], s[a], s[b], n[a], n[b], values);
+    set_plane_kernel<<<grid, block, 0, st>>>(t + idx * s[axis], s[a], s[b], n[a], n[b], values, vnx, vpitch);
     return (int) cudaGetLastError();
 }
 

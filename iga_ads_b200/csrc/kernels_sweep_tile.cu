@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(288, 1)
             double* dst = tiles + (size_t) b * tile_doubles;
             if (CONTIG) {
                 const int lines = min(NL, G.L0 - bx * NL);
-                mbar_expect_tx(&full[b], (uint32_t) (lines * n * 8));
+                mbar_expect_tx(&full[b], (uint32_t) (lines * G.ncopy * 8));
                 const double* src = G.in + (long long) (bx * NL) * G.s0_in + (long long) m * G.s1_in;
                 for (int ln = 0; ln < lines; ++ln)
-                    bulk_g2s(dst + ln * G.pitch, src + ln * G.s0_in, (uint32_t) (n * 8), &full[b]);
+                    bulk_g2s(dst + ln * G.pitch, src + ln * G.s0_in, (uint32_t) (G.ncopy * 8), &full[b]);
             } else {
                 const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(G.maps);
                 mbar_expect_tx(&full[b], (uint32_t) G.load_bytes);
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(288, 1)
             if (CONTIG) {
                 const int lines = min(NL, G.L0 - bx * NL);
                 double* dst = G.out + (long long) (bx * NL) * G.s0_out + (long long) m * G.s1_out;
-                for (int ln = 0; ln < lines; ++ln) bulk_s2g(dst + ln * G.s0_out, src + ln * G.pitch, (uint32_t) (n * 8));
+                for (int ln = 0; ln < lines; ++ln)
+                    bulk_s2g(dst + ln * G.s0_out, src + ln * G.pitch, (uint32_t) (G.ncopy * 8));
             } else {
                 const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(G.maps) + G.nbox_in;
                 for (int k = 0; k < G.nbox_out; ++k) tma_store_3d(maps + k, bx * NL, 0, m, src + G.row0_out[k] * NL);
@@ -179,11 +180,11 @@ __global__ void __launch_bounds__(288, 1)
                 act[r] = lbase + r * NLt + tx < G.L0;
                 const double* mine = tile + (r * NLt + tx) * G.pitch + j0;
 #pragma unroll
-                for (int q = 0; q < CH + KL; q += 2) {  // CH, KL even on this path; pitch and j0 even
+                for (int q = 0; q < CH + KL; q += 2) {  // CH even on this path; pitch and j0 even
                     double2 t2 = make_double2(0.0, 0.0);
                     if (act[r] && j0 + q < n) t2 = *reinterpret_cast<const double2*>(mine + q);
                     v[r][q] = t2.x;
-                    v[r][q + 1] = (j0 + q + 1 < n) ? t2.y : 0.0;
+                    if (q + 1 < CH + KL) v[r][q + 1] = (j0 + q + 1 < n) ? t2.y : 0.0;  // CH + KL is odd for odd KL
                 }
             }
         } else {
@@ -324,16 +325,19 @@ bool encode_tensor_map3(void* map, const double* base, const unsigned long long 
 // caller then uses the register-path kernel), or a CUDA error.
 int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
                       const long long* off_out_h, cudaStream_t st) {
-    static const int NL = [] {
+    // lines per tile: 16 (8 lanes x 2 lines x <= 29 chunks = one CTA); short lines (<= 16 chunks, n <= 288)
+    // take 32 so the CTA still has ~8 warps and the strided tiles move 256 B rows.  ADSB_SWEEP_NL=12|16|32 pins it.
+    static const int NL_env = [] {
         const char* e = getenv("ADSB_SWEEP_NL");
-        const int v = e ? atoi(e) : 16;
-        return v == 12 ? 12 : 16;
+        const int v = e ? atoi(e) : 0;
+        return (v == 12 || v == 16 || v == 32) ? v : 0;
     }();
+    const int NL = NL_env ? NL_env : (F.SC * 16 <= 256 ? 32 : 16);
     const int NLt = NL / SWEEP_RL;
     if (contig && (off_in_h || off_out_h)) return -1;
     const int ncons = (NLt * F.SC + 31) / 32 * 32;
     if (ncons > 256) return -1;
-    if (contig && (SWEEP_CH % 2 || F.KL % 2)) return -1;  // the 128-bit chunk path needs even CH and KL
+    if (contig && SWEEP_CH % 2) return -1;  // the 128-bit chunk path needs an even CH
     auto even = [](long long v) { return (v & 1) == 0; };
     const bool ptr_ok = ((uintptr_t) G.in % 16 == 0) && ((uintptr_t) G.out % 16 == 0);
     SweepTileGeom T{};
@@ -349,7 +353,9 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
     T.ntiles = T.nb0 * G.L1;
     const int rows_needed = F.SC * SWEEP_CH + F.KL;
     if (contig) {
-        if (!ptr_ok || !even(F.n) || !even(G.s0_in) || !even(G.s1_in) || !even(G.s0_out) || !even(G.s1_out)) return -1;
+        if (!ptr_ok || !even(G.s0_in) || !even(G.s1_in) || !even(G.s0_out) || !even(G.s1_out)) return -1;
+        if (!even(F.n) && !G.pad_ok) return -1;  // bulk copies move multiples of 16 B
+        T.ncopy = F.n + (F.n & 1);
         int pitch = rows_needed + (rows_needed & 1);
         while (pitch % 16 != 2) pitch += 2;  // lanes 16 B apart modulo 128 B: conflict-free 128-bit chunk access
         T.pitch = pitch;
@@ -408,7 +414,8 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
     if (nbuf > MAX_NBUF) nbuf = MAX_NBUF;
     T.nbuf = nbuf;
     const size_t smem = (size_t) nbuf * T.tile_doubles * 8 + fixed_bytes;
-    tile_kern_t k = NL == 12 ? pick<12>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
+    tile_kern_t k = NL == 12 ? pick<12>(F.KL, F.piv != 0, contig)
+                    : NL == 32 ? pick<32>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
     if (!k) return -1;
     cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
