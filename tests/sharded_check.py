@@ -31,6 +31,8 @@ def main():
              (2, 30, 1e-7, "p2p", "1", "64"), (3, 21, 1e-7, "p2p", "4", "4"), (2, 30, 1e-7, "nccl", "1", "64")]
     if os.environ.get("ADSB_CHECK_QUICK"):  # default exchange only (large rank counts: keep the box time short)
         cases = cases[:2]
+    if os.environ.get("ADSB_CHECK_CASES"):  # e.g. "3,4,5"
+        cases = [cases[int(k)] for k in os.environ["ADSB_CHECK_CASES"].split(",")]
     for p, ne, dt, mode, chunks, min_planes in cases:
         os.environ["ADSB_SHARDED_EXCHANGE"] = mode
         os.environ["ADSB_SHARDED_CHUNKS"] = chunks
