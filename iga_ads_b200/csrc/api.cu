@@ -336,7 +336,7 @@ int rhs_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view&
     ops.Sx = c->ax[0].d_S;
     ops.My = c->ax[1].d_M;
     ops.Sy = c->ax[1].d_S;
-    ops.MSzT = c->ndim == 3 ? c->ax[2].d_MST : nullptr;
+    ops.MSzT = c->ax[c->ndim - 1].d_MST;  // column table of the marching axis (z in 3-D, y in 2-D)
     RhsGeom g{};
     g.in = in;
     g.out = out;

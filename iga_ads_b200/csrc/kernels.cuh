@@ -109,6 +109,8 @@ int launch_rhs_collapsed(int ndim, const RhsOps& ops, const RhsGeom& G, cudaStre
                          const RhsSide* side = nullptr);
 // TMA-fed 3-D variant (kernels_rhs_tma.cu).  0: launched; -1: not eligible; otherwise a cudaError_t.
 int launch_rhs_tma(const RhsOps& ops, const RhsGeom& G, cudaStream_t st, bool narrow = false);
+// 2-D y-marching variant (ADSB_RHS2D_MARCH=0 disables it); ops.MSzT must hold the column table of axis 1.
+int launch_rhs2d_march(const RhsOps& ops, const RhsGeom& G, cudaStream_t st);
 // Encode a 3-D FP64 tiled tensor map (element strides of dims 1 and 2; dim 0 is contiguous) into *map
 // (a CUtensorMap, 128 bytes, 64 B aligned).  False when the driver entry point is missing or refuses.
 bool encode_tensor_map3(void* map, const double* base, const unsigned long long dims[3],

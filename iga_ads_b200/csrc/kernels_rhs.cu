@@ -516,6 +516,7 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
     const bool fork = split && side && side->side && ndim == 3 && try_tma;
     if (fork && cudaEventRecord(side->fork, st) != cudaSuccess) return (int) cudaGetLastError();
     if (ndim == 3 && try_tma) rc = launch_rhs_tma(ops, g, st);  // -1: not eligible
+    if (ndim == 2 && try_tma) rc = launch_rhs2d_march(ops, g, st);  // -1: not eligible / not enabled
     const bool used_tma = rc != -1;
     if (rc != -1)
         ;
@@ -535,14 +536,14 @@ int launch_p(int ndim, const RhsOps& ops, const RhsGeom& g0, cudaStream_t st, bo
     const long long cols = (long long) rem * e.out_n[1];
     dim3 eb(128, 1, 1), eg((unsigned) ((cols + 127) / 128), ndim == 3 ? (e.out_n[2] + EDGE_ZSEG - 1) / EDGE_ZSEG : 1, 1);
     // the remainder kernel may run next to the main kernel on the caller's side stream (fork / join)
-    const bool forked = fork && used_tma;
+    const bool forked = fork && used_tma;  // (fork implies ndim == 3)
     cudaStream_t es = forked ? side->side : st;
     if (forked) {
         cudaError_t ce = cudaStreamWaitEvent(side->side, side->fork, 0);
         if (ce != cudaSuccess) return (int) ce;
     }
     rc = -1;
-    if (used_tma) rc = launch_rhs_tma(ops, e, es, true);  // same kernel, 8-pair-wide warps; -1: not eligible
+    if (used_tma && ndim == 3) rc = launch_rhs_tma(ops, e, es, true);  // same kernel, 8-pair-wide warps; -1: not eligible
     if (rc == -1) {
         if (ndim == 3)
             rhs_edge_kernel<P, true><<<eg, eb, 0, es>>>(ops, e);

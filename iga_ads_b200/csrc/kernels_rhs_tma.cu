@@ -411,7 +411,203 @@ int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 2-D variant (ADSB_RHS2D_MARCH=0 switches back to the cp.async kernel):
+//     rhs = (Kx (x) My) c - beta_y (Mx (x) Sy) c,   Kx = alpha Mx - beta_x Sx
+// (examples/heat/heat_2d.hpp:80-106, implicit/implicit.hpp:132-182).  The cp.async kernel does one 64 x 8 tile
+// per CTA with no pipelining (0.41 ms at 4099^2, p=3, against a 0.04 ms roofline; this kernel: 0.093 ms, and
+// 0.057 instead of 0.162 ms at 4096^2, p=2).  Here a CTA owns a strip of
+// 64*NWARP x values and MARCHES along y: row blocks of W = 2p+1 rows arrive by TMA (ring of NSTAGE), a thread
+// does the x product of its two x out of a 128-bit shared window and scatters the row onto 2p+1 partial
+// output rows in registers (rotation = position of the row in its block: compile time).  No data moves
+// between threads, so the only barrier is the one that frees a ring slot.
+template <int P, int NWARP, int NSTAGE, bool FORCING>
+__global__ void __launch_bounds__(NWARP * 32)
+    rhs2d_march_kernel(const __grid_constant__ CUtensorMap tmap, const RhsOps ops, const RhsGeom g, int yseg) {
+    constexpr int W = 2 * P + 1, PH = P + (P & 1), NTH = NWARP * 32, TXW = 64 * NWARP, RW = TXW + 2 * PH;
+    constexpr uint32_t STAGE_BYTES = RW * W * 8, STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base_u = (smem_addr(smem_raw) + 127u) & ~127u;
+    unsigned char* base_p = smem_raw + (base_u - smem_addr(smem_raw));
+    const uint32_t raw_u = base_u;                          // [NSTAGE][W rows][RW]
+    const uint32_t bar_u = raw_u + NSTAGE * STAGE_STRIDE;   // NSTAGE mbarriers
+    const uint32_t yt_u = bar_u + NSTAGE * 8 + ((NSTAGE & 1) ? 8 : 0);  // [rows][W] double2 (My, -beta_y Sy) columns
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_p + (bar_u - base_u));
+    double2* yt = reinterpret_cast<double2*>(base_p + (yt_u - base_u));
+
+    const int tid = threadIdx.x;
+    const int x0 = g.out_lo[0] + blockIdx.x * TXW;
+    const int nx = ops.n[0];
+    const int ys = g.out_lo[1] + blockIdx.y * yseg;
+    const int ye = min(ys + yseg, g.out_lo[1] + g.out_n[1]);
+    const int kb = ys - P;
+    const int NR = ye - ys + 2 * P;          // input rows kb .. kb + NR - 1
+    const int NB = (NR + W - 1) / W;         // row blocks
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    {   // the column table carries P zero rows on both sides; rows past NR (tail of the last block) read as zero
+        const double* yr = ops.MSzT + (long long) (kb + P) * 2 * (W + 1);
+        for (int i = tid; i < NB * W * W; i += NTH) {
+            const int q = i / W, d = i - q * W;
+            yt[i] = q < NR ? make_double2(yr[q * 2 * (W + 1) + d], -g.beta[1] * yr[q * 2 * (W + 1) + (W + 1) + d])
+                           : make_double2(0.0, 0.0);
+        }
+    }
+    double kx[2][W], mx[2][W];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int gxc = min(x0 + 2 * tid + b, nx - 1);
+#pragma unroll
+        for (int m = 0; m < W; ++m) {
+            const double a = ops.Mx[gxc * W + m], sv = ops.Sx[gxc * W + m];
+            mx[b][m] = a;
+            kx[b][m] = g.alpha * a - g.beta[0] * sv;
+        }
+    }
+    __syncthreads();
+
+    const int c0 = x0 - PH - g.in_lo[0], c1b = kb - g.in_lo[1];
+    auto issue = [&](int blk, int stage) {  // rows kb + blk*W .. +W-1 (outside the array: zero-filled)
+        mbar_expect_tx_u32(bar_u + stage * 8, STAGE_BYTES);
+        tma_load_box3(raw_u + stage * STAGE_STRIDE, &tmap, c0, c1b + blk * W, 0, bar_u + stage * 8);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s)
+            if (s < NB) issue(s, s);
+    }
+
+    const int gx = x0 + 2 * tid;
+    const bool live = gx < g.out_lo[0] + g.out_n[0];
+    double* o_row = g.out + (gx - g.out_lo[0]) + (long long) (ys - g.out_lo[1]) * g.so[1];
+    const double* f_row = FORCING ? g.forcing + (gx - g.out_lo[0]) + (long long) (ys - g.out_lo[1]) * g.so[1] : nullptr;
+
+    double acc[2][W];
+#pragma unroll
+    for (int xb = 0; xb < 2; ++xb)
+#pragma unroll
+        for (int sl = 0; sl < W; ++sl) acc[xb][sl] = 0.0;
+
+    int stage = 0;
+    uint32_t parity = 0, yrow_u = yt_u;
+    for (int blk = 0; blk < NB; ++blk) {
+        mbar_wait_u32(bar_u + stage * 8, parity);
+        const uint32_t rs = raw_u + stage * STAGE_STRIDE + (uint32_t) (2 * tid) * 8;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int q = blk * W + j;  // input row kb + q, rotation j
+            double win[2 * PH + 2];
+#pragma unroll
+            for (int c = 0; c < 2 * PH + 2; c += 2) {
+                const double2 t = lds2(rs + (uint32_t) (j * RW + c) * 8);
+                win[c] = t.x;
+                win[c + 1] = t.y;
+            }
+            double pv[2], qv[2];
+#pragma unroll
+            for (int xb = 0; xb < 2; ++xb) {
+                pv[xb] = kx[xb][0] * win[xb + PH - P];
+                qv[xb] = mx[xb][0] * win[xb + PH - P];
+#pragma unroll
+                for (int m = 1; m < W; ++m) {
+                    pv[xb] = fma(kx[xb][m], win[xb + PH - P + m], pv[xb]);
+                    qv[xb] = fma(mx[xb][m], win[xb + PH - P + m], qv[xb]);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < W; ++d) {
+                const double2 cy = lds2(yrow_u + (uint32_t) ((j * W + d) * 16));
+                const int sl = (d + j) % W;
+#pragma unroll
+                for (int xb = 0; xb < 2; ++xb) {
+                    acc[xb][sl] = fma(cy.x, pv[xb], acc[xb][sl]);
+                    acc[xb][sl] = fma(cy.y, qv[xb], acc[xb][sl]);
+                }
+            }
+            if (q >= 2 * P && q < NR) {  // output row ys + q - 2P is complete
+                if (live) {
+                    double v0 = acc[0][j], v1 = acc[1][j];
+                    if (FORCING) {
+                        const double2 f = __ldg(reinterpret_cast<const double2*>(f_row));
+                        v0 = fma(g.gamma, f.x, v0);
+                        v1 = fma(g.gamma, f.y, v1);
+                    }
+                    __stcs(reinterpret_cast<double2*>(o_row), make_double2(v0, v1));
+                }
+                o_row += g.so[1];
+                if (FORCING) f_row += g.so[1];
+            }
+            acc[0][j] = 0.0;
+            acc[1][j] = 0.0;
+        }
+        yrow_u += W * W * 16;
+        __syncthreads();  // every thread is done with this ring slot
+        if (tid == 0 && blk + NSTAGE < NB) issue(blk + NSTAGE, stage);
+        if (++stage == NSTAGE) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+}
+
+template <int P, int NWARP, int NSTAGE>
+int launch_2d_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
+    constexpr int W = 2 * P + 1, PH = P + (P & 1), TXW = 64 * NWARP, RW = TXW + 2 * PH;
+    constexpr int STAGE_STRIDE = (RW * W * 8 + 127) / 128 * 128;
+    auto kern = g.forcing ? rhs2d_march_kernel<P, NWARP, NSTAGE, true> : rhs2d_march_kernel<P, NWARP, NSTAGE, false>;
+    CUtensorMap map;
+    const unsigned long long dims[3] = {(unsigned long long) g.in_n[0], (unsigned long long) g.in_n[1], 1ull};
+    const unsigned long long strides[2] = {(unsigned long long) g.si[1], (unsigned long long) g.si[1] * g.in_n[1]};
+    const unsigned box[3] = {(unsigned) RW, (unsigned) W, 1u};
+    if (RW > 256 || !encode_tensor_map3(&map, g.in, dims, strides, box)) return -1;
+    const int tx = (g.out_n[0] + TXW - 1) / TXW;
+    const int fixed = NSTAGE * STAGE_STRIDE + NSTAGE * 8 + 8 + 128;
+    // y segments: ~3 CTAs per SM worth of strips, each at least 16 p rows long and short enough for its table
+    const int cap = (64 * 1024 - fixed) / (W * 16) - 2 * P - W;
+    const long long slots = 3ll * ((g.max_sms > 0 && g.max_sms < sm_count_tma()) ? g.max_sms : sm_count_tma());
+    int nseg = (int) ((slots + tx - 1) / tx);
+    if (nseg < 1) nseg = 1;
+    int yseg = (g.out_n[1] + nseg - 1) / nseg;
+    if (yseg < 16 * P) yseg = 16 * P < g.out_n[1] ? 16 * P : g.out_n[1];
+    if (yseg > cap) yseg = cap;
+    if (yseg < 1) return -1;
+    nseg = (g.out_n[1] + yseg - 1) / yseg;
+    const int nb = (yseg + 2 * P + W - 1) / W;
+    const int smem = fixed + nb * W * W * 16;
+    cudaError_t e = cudaFuncSetAttribute((const void*) kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int) e;
+    dim3 grid(tx, nseg, 1), block(NWARP * 32, 1, 1);
+    kern<<<grid, block, smem, st>>>(map, ops, g, yseg);
+    return (int) cudaGetLastError();
+}
+
 }  // namespace
+
+// 2-D marching kernel.  0: launched; -1: not eligible / not enabled; else a cudaError_t.
+int launch_rhs2d_march(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
+    static const bool enabled = [] {
+        const char* e = getenv("ADSB_RHS2D_MARCH");
+        return !e || atoi(e) != 0;
+    }();
+    if (!enabled || !ops.MSzT) return -1;
+    const int p = ops.p[0];
+    if (ops.p[1] != p) return -1;
+    auto even = [](long long v) { return (v & 1) == 0; };
+    if (g.si[0] != 1 || g.so[0] != 1 || !even(g.si[1]) || !even(g.so[1])) return -1;
+    if (!even(g.out_n[0]) && !(g.out_lo[0] + g.out_n[0] == ops.n[0] && g.so[1] > g.out_n[0])) return -1;
+    if ((uintptr_t) g.in % 16 || (uintptr_t) g.out % 16 || (g.forcing && (uintptr_t) g.forcing % 16)) return -1;
+    for (int d = 0; d < 2; ++d)
+        if (g.in_lo[d] < 0 || g.in_lo[d] + g.in_n[d] > ops.n[d]) return -1;
+    switch (p) {
+    case 2: return launch_2d_cfg<2, 3, 4>(ops, g, st);   // strips of 192 x (raw row 196 doubles <= TMA box limit 256)
+    case 3: return launch_2d_cfg<3, 3, 4>(ops, g, st);
+    default: return -1;
+    }
+}
 
 // 0: launched; -1: this problem is not eligible (caller uses the cp.async kernel); else a cudaError_t.
 // narrow: the output box is at most 16 columns wide (x remainder of the 64-wide tiling): 8-pair-wide warps.
