@@ -73,6 +73,8 @@ _SIGNATURES = {
     "adsb_basis_tables": (c_int, [c_int, c_int, c_dbl, c_dbl, c_int, c_int, dp, dp, dp, dp, ip]),
     "adsb_matrix_1d": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int, dp]),
     "adsb_band_factorize": (c_int, [c_int, c_int, c_int, dp, c_int, ip]),
+    "adsb_segment_bounds": (c_int, [c_int, c_int, ip, c_int, c_int, ip]),
+    "adsb_segment_plan": (c_int, [c_int, c_int, c_int, c_int, dp, ip, c_int, ip, c_dbl, ip, dp, dp, dp, dp, dp]),
     "adsb_create": (c_int, [c_int, ip, ip, ip, c_int, ctypes.POINTER(vp)]),
     "adsb_destroy": (c_int, [vp]),
     "adsb_set_stream": (c_int, [vp, vp]),

@@ -429,6 +429,207 @@ int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const in
     return ADSB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Segmented substitution.  With L, U the (row-interchanged) band factors and a segment s = rows
+// [a, b) whose boundary no interchange crosses, the sequential dgbtrs recurrence splits exactly into
+//     xhat_s  = solve of the segment alone (its own columns of the factor, zero incoming states)
+//     din_s   = forward updates that the columns left of a apply to rows a .. a+KL-1
+//     tin_s   = true unknowns b .. b+KD-1
+//     x_s     = xhat_s + Xi_s din_s + Psi_s tin_s
+// chained by  din_{s+1} = E_s xhat_s[last KL] + T_s din_s   and   tin_{s-1} = xhat_s[first KD] + Xi_s[first KD] din_s
+// + Psi_s[first KD] tin_s.  E, T, Xi, Psi depend only on the factor; the chains are expanded to the depth at
+// which the products of T (of Psi[first KD]) drop below `tol`.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct BandRows {  // per column j: multipliers, U row (super-diagonals), diagonal, pivot offset
+    int n, kl, kd;
+    std::vector<double> Lm, Ut, diag;
+    std::vector<int> pv;
+};
+int unpack_factor(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, BandRows& B) {
+    const int kd = kl + ku;
+    B.n = n; B.kl = kl; B.kd = kd;
+    B.Lm.assign(static_cast<size_t>(n) * std::max(kl, 1), 0.0);
+    B.Ut.assign(static_cast<size_t>(n) * std::max(kd, 1), 0.0);
+    B.diag.assign(n, 0.0);
+    B.pv.assign(n, 0);
+    auto Aat = [&](int r, int c) { return ab[static_cast<size_t>(c) * ldab + r]; };
+    for (int j = 0; j < n; ++j) {
+        const int t = ipiv[j] - 1 - j;
+        if (t < 0 || t > kl || j + t >= n) return fail(ADSB_EINVAL, "factor: bad pivot vector");
+        B.pv[j] = t;
+        const int lm = std::min(kl, n - 1 - j);
+        for (int i = 0; i < lm; ++i) B.Lm[static_cast<size_t>(j) * kl + i] = Aat(kd + 1 + i, j);
+        for (int k = 1; k <= kd && j + k < n; ++k) B.Ut[static_cast<size_t>(j) * kd + k - 1] = Aat(kd - k, j + k);
+        B.diag[j] = Aat(kd, j);
+        if (B.diag[j] == 0) return fail(ADSB_ESINGULAR, "factor: zero diagonal in U at column " + std::to_string(j + 1));
+    }
+    return ADSB_OK;
+}
+bool clean_cut(const BandRows& B, int a) {  // no interchange of a column left of a reaches row a or beyond
+    for (int j = std::max(0, a - B.kl); j < a; ++j)
+        if (j + B.pv[j] >= a) return false;
+    return true;
+}
+void matmul_rect(int R, int K, int C, const double* A, const double* Bm, double* Cm) {  // (R x K) * (K x C)
+    for (int r = 0; r < R; ++r)
+        for (int c = 0; c < C; ++c) {
+            double acc = 0;
+            for (int m = 0; m < K; ++m) acc += A[r * K + m] * Bm[m * C + c];
+            Cm[r * C + c] = acc;
+        }
+}
+}  // namespace
+
+int pick_segment_bounds(int n, int kl, const int* ipiv, int S, int align, int min_rows, int* bounds) {
+    if (S < 1 || n < 1) return fail(ADSB_EINVAL, "segments: bad count");
+    BandRows B;
+    B.n = n; B.kl = kl; B.kd = 0;
+    B.pv.assign(n, 0);
+    for (int j = 0; j < n; ++j) {
+        const int t = ipiv[j] - 1 - j;
+        if (t < 0 || t > kl || j + t >= n) return fail(ADSB_EINVAL, "factor: bad pivot vector");
+        B.pv[j] = t;
+    }
+    if (align < 1) align = 1;
+    bounds[0] = 0;
+    bounds[S] = n;
+    for (int s = 1; s < S; ++s) {
+        // target: balanced cut, rounded to the alignment; then the nearest clean row (alternating search)
+        const long long ideal = static_cast<long long>(n) * s / S;
+        int target = static_cast<int>((ideal + align / 2) / align * align);
+        int found = -1;
+        auto usable = [&](int a) { return a > bounds[s - 1] && a < n && clean_cut(B, a); };
+        for (int d = 0; d <= 2 && found < 0 && align > 1; ++d)  // aligned candidates first
+            for (int sgn = -1; sgn <= 1 && found < 0; sgn += 2)
+                if (usable(target + sgn * d * align)) found = target + sgn * d * align;
+        for (int d = 0; d <= 4 * kl + align && found < 0; ++d)
+            for (int sgn = -1; sgn <= 1 && found < 0; sgn += 2)
+                if (usable(target + sgn * d)) found = target + sgn * d;
+        if (found < 0) return fail(ADSB_EINVAL, "segments: no cut free of row interchanges near row " + std::to_string(target));
+        bounds[s] = found;
+    }
+    for (int s = 0; s < S; ++s)
+        if (bounds[s + 1] - bounds[s] < min_rows) return fail(ADSB_EINVAL, "segments: a segment is shorter than the band");
+    return ADSB_OK;
+}
+
+int build_segment_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int S, const int* bounds,
+                       double tol, SegPlan& P) {
+    BandRows B;
+    if (int rc = unpack_factor(n, kl, ku, ldab, ab, ipiv, B)) return rc;
+    const int kd = B.kd;
+    bool piv = false;
+    int kd_eff = 0;
+    for (int j = 0; j < n; ++j) {
+        if (B.pv[j]) piv = true;
+        for (int k = 1; k <= kd; ++k)
+            if (B.Ut[static_cast<size_t>(j) * kd + k - 1] != 0) kd_eff = std::max(kd_eff, k);
+    }
+    // same (KL, KD) variant as build_sweep_plan picks for the whole factor
+    const int var = piv ? std::max({kl, (kd_eff + 1) / 2, 1}) : std::max({kl, kd_eff, 1});
+    const int KL = var, KD = piv ? 2 * var : var;
+    if (S < 1 || bounds[0] != 0 || bounds[S] != n) return fail(ADSB_EINVAL, "segments: bounds must run from 0 to n");
+    for (int s = 0; s < S; ++s) {
+        if (bounds[s + 1] - bounds[s] < std::max(KL, KD)) return fail(ADSB_EINVAL, "segments: a segment is shorter than the band");
+        if (s && !clean_cut(B, bounds[s])) return fail(ADSB_EINVAL, "segments: a row interchange crosses a segment boundary");
+    }
+    P = SegPlan{};
+    P.n = n; P.KL = KL; P.KD = KD; P.piv = piv ? 1 : 0; P.S = S;
+    P.bounds.assign(bounds, bounds + S + 1);
+    const int KC = KD + KL;
+    P.cf.assign(static_cast<size_t>(n) * KC, 0.0);
+    P.E.assign(static_cast<size_t>(S) * KL * KL, 0.0);
+    P.XiF.assign(static_cast<size_t>(S) * KD * KL, 0.0);
+    std::vector<double> T(static_cast<size_t>(S) * KL * KL, 0.0), R(static_cast<size_t>(S) * KD * KD, 0.0);
+    auto Lm = [&](int j, int m) { return m <= kl ? B.Lm[static_cast<size_t>(j) * kl + m - 1] : 0.0; };  // m = 1..
+    auto Ut = [&](int j, int m) { return m <= kd ? B.Ut[static_cast<size_t>(j) * kd + m - 1] : 0.0; };
+    for (int s = 0; s < S; ++s) {
+        const int a = bounds[s], b = bounds[s + 1], ns = b - a;
+        std::vector<double> win(ns + KL), xs(ns + KD), phi(ns);
+        for (int r = 0; r < KL; ++r) {  // unit forward in-state on row a + r
+            std::fill(win.begin(), win.end(), 0.0);
+            win[r] = 1.0;
+            for (int i = 0; i < ns; ++i) {
+                const int j = a + i, t = B.pv[j];
+                if (t) std::swap(win[i], win[i + t]);
+                for (int m = 1; m <= KL; ++m)
+                    if (j + m < n) win[i + m] = std::fma(-Lm(j, m), win[i], win[i + m]);
+                phi[i] = win[i];
+            }
+            for (int m = 0; m < KL; ++m) T[(static_cast<size_t>(s) * KL + m) * KL + r] = win[ns + m];
+            std::fill(xs.begin(), xs.end(), 0.0);
+            for (int i = ns - 1; i >= 0; --i) {
+                const int j = a + i;
+                double acc = phi[i];
+                for (int m = KD; m >= 1; --m)
+                    if (i + m < ns) acc = std::fma(-Ut(j, m), xs[i + m], acc);
+                xs[i] = acc / B.diag[j];
+                P.cf[static_cast<size_t>(j) * KC + KD + r] = xs[i];
+            }
+            for (int i = 0; i < KD; ++i) P.XiF[(static_cast<size_t>(s) * KD + i) * KL + r] = xs[i];
+        }
+        for (int k = 0; k < KD; ++k) {  // unit value of unknown b + k
+            std::fill(xs.begin(), xs.end(), 0.0);
+            xs[ns + k] = 1.0;
+            for (int i = ns - 1; i >= 0; --i) {
+                const int j = a + i;
+                double acc = 0;
+                for (int m = KD; m >= 1; --m) acc = std::fma(-Ut(j, m), xs[i + m], acc);
+                xs[i] = acc / B.diag[j];
+                P.cf[static_cast<size_t>(j) * KC + k] = xs[i];
+            }
+            for (int i = 0; i < KD; ++i) R[(static_cast<size_t>(s) * KD + i) * KD + k] = xs[i];
+        }
+        // E_s = (updates of rows b .. b+KL-1 by the last KL columns) * (U restricted to the last KL rows)
+        std::vector<double> Lout(KL * KL, 0.0), Ul(KL * KL, 0.0);
+        for (int ii = 0; ii < KL; ++ii) {
+            const int j = b - KL + ii;
+            Ul[ii * KL + ii] = B.diag[j];
+            for (int m = 1; ii + m < KL; ++m) Ul[ii * KL + ii + m] = Ut(j, m);
+            for (int k = 0; k < KL; ++k) {
+                const int m = b + k - j;
+                if (m >= 1 && m <= KL && b + k < n) Lout[k * KL + ii] = -Lm(j, m);
+            }
+        }
+        matmul_rect(KL, KL, KL, Lout.data(), Ul.data(), &P.E[static_cast<size_t>(s) * KL * KL]);
+    }
+    if (maxabs(T.data(), static_cast<int>(T.size())) > 1.0 || maxabs(R.data(), static_cast<int>(R.size())) > 1.0)
+        return fail(ADSB_EINVAL, "segments: the factor's boundary responses grow (not diagonally dominant enough)");
+    // chain products: din_s = Dseg_{s-1} + T_{s-1} Dseg_{s-2} + T_{s-1} T_{s-2} Dseg_{s-3} + ...
+    auto chain = [&](int K, const std::vector<double>& M, bool forward, std::vector<double>& out) {
+        const int Dmax = std::max(1, S - 1);
+        std::vector<std::vector<double>> prod(static_cast<size_t>(S) * Dmax);
+        int depth = 1;
+        std::vector<double> cur(K * K), nxt(K * K);
+        for (int s = 0; s < S; ++s) {
+            std::fill(cur.begin(), cur.end(), 0.0);
+            for (int i = 0; i < K; ++i) cur[i * K + i] = 1.0;
+            for (int d = 1; d <= Dmax; ++d) {
+                const int src = forward ? s - d : s + d;  // segment whose state term d multiplies
+                if (src < 0 || src >= S) break;
+                if (d > 1 && maxabs(cur.data(), K * K) < tol) break;
+                prod[static_cast<size_t>(s) * Dmax + d - 1] = cur;
+                depth = std::max(depth, d);
+                // next: multiply by the transfer of segment `src` (forward: on the right; backward: on the right too)
+                matmul(K, cur.data(), &M[static_cast<size_t>(src) * K * K], nxt.data());
+                std::swap(cur, nxt);
+            }
+        }
+        out.assign(static_cast<size_t>(S) * depth * K * K, 0.0);
+        for (int s = 0; s < S; ++s)
+            for (int d = 0; d < depth; ++d) {
+                const auto& m = prod[static_cast<size_t>(s) * Dmax + d];
+                if (!m.empty()) std::copy(m.begin(), m.end(), &out[(static_cast<size_t>(s) * depth + d) * K * K]);
+            }
+        return depth;
+    };
+    P.DF = chain(KL, T, true, P.Wf);
+    P.DB = chain(KD, R, false, P.Vb);
+    return ADSB_OK;
+}
+
 }  // namespace adsb
 
 // ------------------------------------- C ABI (host part) --------------------------------------
@@ -464,6 +665,31 @@ int adsb_matrix_1d(int kind, int p, int elements, double a, double b, double h, 
 
 int adsb_band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv) {
     return adsb::band_factorize(n, kl, ku, ab, ldab, ipiv);
+}
+
+int adsb_segment_bounds(int n, int kl, const int* ipiv, int nseg, int align, int* bounds) {
+    if (!ipiv || !bounds) return adsb::fail(ADSB_EINVAL, "segment_bounds: null argument");
+    return adsb::pick_segment_bounds(n, kl, ipiv, nseg, align, 1, bounds);
+}
+
+int adsb_segment_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int nseg, const int* bounds,
+                      double tol, int* dims, double* E, double* Wf, double* Vb, double* XiF, double* cf) {
+    if (!ab || !ipiv || !bounds) return adsb::fail(ADSB_EINVAL, "segment_plan: null argument");
+    adsb::SegPlan P;
+    if (int rc = adsb::build_segment_plan(n, kl, ku, ldab, ab, ipiv, nseg, bounds, tol > 0 ? tol : 1e-20, P)) return rc;
+    if (dims) {
+        const int d[8] = {P.KL, P.KD, P.piv, P.S, P.DF, P.DB, P.n, 0};
+        std::copy(d, d + 8, dims);
+    }
+    auto put = [](double* dst, const std::vector<double>& v) {
+        if (dst) std::copy(v.begin(), v.end(), dst);
+    };
+    put(E, P.E);
+    put(Wf, P.Wf);
+    put(Vb, P.Vb);
+    put(XiF, P.XiF);
+    put(cf, P.cf);
+    return ADSB_OK;
 }
 
 }  // extern "C"

@@ -39,6 +39,26 @@ struct SweepPlan {
 int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch, int group,
                      SweepPlan& plan);
 
+// Segmented substitution (host_setup.cpp): a line is cut into S segments [bounds[s], bounds[s+1]); every
+// segment is solved on its own (the same factor restricted to the segment, zero incoming states) and the
+// exact dgbtrs result is recovered from KL + KD boundary values per segment and line.  Segments are the
+// slabs of a sharded run (one per GPU) or the pieces of a line too long for one CTA.
+struct SegPlan {
+    int n = 0, KL = 0, KD = 0, piv = 0, S = 0;
+    int DF = 1, DB = 1;        // chain depths: din_s uses segments s-1 .. s-DF, tin_s uses s+1 .. s+DB
+    std::vector<int> bounds;   // [S+1]
+    std::vector<double> E;     // [S][KL][KL]      Dseg_s = E_s * xhat_s[last KL rows]
+    std::vector<double> Wf;    // [S][DF][KL][KL]  din_s = sum_d Wf[s][d-1] * Dseg_{s-d}   (Wf[s][0] = I)
+    std::vector<double> Vb;    // [S][DB][KD][KD]  tin_s = sum_d Vb[s][d-1] * X_{s+d}      (Vb[s][0] = I)
+    std::vector<double> XiF;   // [S][KD][KL]      X_s = xhat_s[first KD rows] + XiF_s * din_s
+    std::vector<double> cf;    // [n][KD+KL]       x_j = xhat_j + Psi(j,:) tin_s + Xi(j,:) din_s
+};
+// Balanced segment boundaries that no row interchange of the factor crosses (and, when align > 1, that are
+// multiples of `align` where possible).  Returns ADSB_EINVAL when no such cut exists near a target.
+int pick_segment_bounds(int n, int kl, const int* ipiv, int S, int align, int min_rows, int* bounds);
+int build_segment_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int S, const int* bounds,
+                       double tol, SegPlan& plan);
+
 }  // namespace adsb
 
 #endif

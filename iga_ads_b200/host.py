@@ -73,6 +73,33 @@ def band_factorize(ab, kl, ku):
     return lu, ipiv
 
 
+def segment_bounds(ipiv, kl, nseg, align=1):
+    """Balanced cuts of a line into `nseg` segments that no row interchange of the factor crosses."""
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    bounds = np.zeros(nseg + 1, dtype=np.int32)
+    check(_lib.load().adsb_segment_bounds(len(ipiv), kl, i_(ipiv), nseg, align, i_(bounds)))
+    return bounds
+
+
+def segment_plan(lu, ipiv, kl, ku, bounds, tol=0.0):
+    """Tables of the segmented substitution (see adsb_segment_plan in include/adsb200.h)."""
+    lu = np.ascontiguousarray(lu, dtype=np.float64)
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    bounds = np.ascontiguousarray(bounds, dtype=np.int32)
+    n, S = lu.shape[0], len(bounds) - 1
+    dims = np.zeros(8, dtype=np.int32)
+    lib = _lib.load()
+    check(lib.adsb_segment_plan(n, kl, ku, lu.shape[1], d_(lu), i_(ipiv), S, i_(bounds), tol, i_(dims),
+                                None, None, None, None, None))
+    KL, KD, piv, _, DF, DB = (int(v) for v in dims[:6])
+    t = dict(KL=KL, KD=KD, piv=piv, S=S, DF=DF, DB=DB, bounds=bounds, E=np.zeros((S, KL, KL)),
+             Wf=np.zeros((S, DF, KL, KL)), Vb=np.zeros((S, DB, KD, KD)), XiF=np.zeros((S, KD, KL)),
+             cf=np.zeros((n, KD + KL)))
+    check(lib.adsb_segment_plan(n, kl, ku, lu.shape[1], d_(lu), i_(ipiv), S, i_(bounds), tol, i_(dims),
+                                d_(t["E"]), d_(t["Wf"]), d_(t["Vb"]), d_(t["XiF"]), d_(t["cf"])))
+    return t
+
+
 @dataclass
 class dim_config:
     """include/ads/simulation/config.hpp:11-31"""

@@ -230,6 +230,24 @@ int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int
                     int* pv, double* cfF, double* cfB, double* cfC, double* T, double* Rm, double* W,
                     double* V);
 
+/* ================== segmented substitution (long lines, slab-sharded sweeps) =================
+ * dgbtrs over a line cut into segments [bounds[s], bounds[s+1]): every segment is solved alone with the
+ * factor's own columns (pass A: an ordinary sweep with the segment's factor), then corrected with KL + KD
+ * boundary values per segment and line (pass B).  Algebraically the recurrence of
+ * lin::solve_with_factorized -> dgbtrs_ (include/ads/lin/band_solve.hpp:21-31) with the same factor and
+ * pivots; segments are the z-slabs of a sharded run (one per GPU: only the boundary values cross NVLink,
+ * no transpose) or the pieces of a line too long for one CTA (heat_2d 4096^2). */
+
+/* Balanced cuts that no row interchange of the factor crosses, multiples of `align` where possible;
+ * bounds[nseg+1].  Host only. */
+int adsb_segment_bounds(int n, int kl, const int* ipiv, int nseg, int align, int* bounds);
+
+/* Introspection (CPU tests): the segment tables exactly as adsb_set_axis_segments builds them.
+ * dims[8] = {KL, KD, piv, S, DF, DB, n, 0}; E[S*KL*KL], Wf[S*DF*KL*KL], Vb[S*DB*KD*KD], XiF[S*KD*KL],
+ * cf[n*(KD+KL)] (Psi | Xi per row); any output may be NULL.  tol <= 0: default chain cut-off 1e-20. */
+int adsb_segment_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int nseg, const int* bounds,
+                      double tol, int* dims, double* E, double* Wf, double* Vb, double* XiF, double* cf);
+
 #ifdef __cplusplus
 }
 #endif
