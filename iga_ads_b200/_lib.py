@@ -85,6 +85,8 @@ _SIGNATURES = {
     "adsb_set_axis_factor": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_int, dp, ip]),
     "adsb_upload": (c_int, [vp, c_int, dp]),
     "adsb_download": (c_int, [vp, c_int, dp]),
+    "adsb_upload_async": (c_int, [vp, c_int, vp, vp]),
+    "adsb_download_async": (c_int, [vp, c_int, vp, vp]),
     "adsb_swap": (c_int, [vp, c_int, c_int]),
     "adsb_zero": (c_int, [vp, c_int]),
     "adsb_bind": (c_int, [vp, c_int, vp]),
@@ -102,6 +104,16 @@ _SIGNATURES = {
     "adsb_launch_count": (c_ll, [vp]),
     "adsb_sweep_view": (c_int, [vp, c_int, c_int, vp, ctypes.POINTER(View), llp, vp, ctypes.POINTER(View), llp]),
     "adsb_sweep_plan": (c_int, [c_int, c_int, c_int, c_int, dp, ip, ip, ip, dp, dp, dp, dp, dp, dp, dp]),
+    "adsb_set_axis_segments": (c_int, [vp, c_int, c_int, c_int, ip, c_int, c_int]),
+    "adsb_segment_info": (c_int, [vp, c_int, c_int, ip]),
+    "adsb_seg_sweep_view": (c_int, [vp, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp, ctypes.POINTER(View)]),
+    "adsb_seg_dseg_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View),
+                                   ctypes.POINTER(vp), c_int]),
+    "adsb_seg_din_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp, vp,
+                                  ctypes.POINTER(vp), c_int]),
+    "adsb_seg_tin": (c_int, [vp, c_int, c_int, c_int, c_int, c_ll, vp, vp]),
+    "adsb_seg_correct_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp,
+                                      ctypes.POINTER(View), vp, vp]),
     "adsb_rhs_view": (c_int, [vp, ctypes.POINTER(Form), vp, ctypes.POINTER(View), ip, vp, vp,
                               ctypes.POINTER(View), ip]),
 }

@@ -17,10 +17,24 @@ using namespace adsb;
 
 namespace {
 
+struct SegSet {  // adsb_set_axis_segments: tables + the pass-A factor of every local segment
+    bool set = false;
+    SegDev dev{};
+    std::vector<int> bounds;
+    int local_lo = 0, local_cnt = 0;
+    std::vector<SweepFactor> local;  // [local_cnt]
+    std::vector<void*> allocs;
+};
+
 struct DevFactor {
     bool set = false;
     SweepFactor f{};
     std::vector<void*> allocs;
+    // host copy of the dgbtrf output (segments are cut from it later)
+    int n = 0, kl = 0, ku = 0, ldab = 0;
+    std::vector<double> ab;
+    std::vector<int> ipiv;
+    SegSet seg;
 };
 
 struct AxisData {
@@ -95,10 +109,31 @@ int upload_vec(const std::vector<T>& h, size_t padded, T** d, std::vector<void*>
     return ADSB_OK;
 }
 
+void free_segments(SegSet& g) {
+    for (void* p : g.allocs) cudaFree(p);
+    g = SegSet{};
+}
+
 void free_factor(DevFactor& f) {
     for (void* p : f.allocs) cudaFree(p);
     f.allocs.clear();
     f.set = false;
+    free_segments(f.seg);
+}
+
+int upload_plan(const SweepPlan& P, SweepFactor& out, std::vector<void*>& allocs) {
+    double *cfF, *cfB, *cfC, *T, *Rm, *W, *V;
+    int* pv;
+    if (int rc = upload_vec(P.cfF, 0, &cfF, &allocs)) return rc;
+    if (int rc = upload_vec(P.cfB, 0, &cfB, &allocs)) return rc;
+    if (int rc = upload_vec(P.cfC, 0, &cfC, &allocs)) return rc;
+    if (int rc = upload_vec(P.pv, 0, &pv, &allocs)) return rc;
+    if (int rc = upload_vec(P.T, 0, &T, &allocs)) return rc;
+    if (int rc = upload_vec(P.Rm, 0, &Rm, &allocs)) return rc;
+    if (int rc = upload_vec(P.W, 0, &W, &allocs)) return rc;
+    if (int rc = upload_vec(P.V, 0, &V, &allocs)) return rc;
+    out = SweepFactor{cfF, cfB, cfC, pv, T, Rm, W, V, P.n, P.ST, P.SC, P.KL, P.KD, P.piv, P.DF, P.DB, P.seq};
+    return ADSB_OK;
 }
 
 int ensure_buf(adsb_ctx* c, int b) {
@@ -175,11 +210,11 @@ int get_offsets(adsb_ctx* c, const long long* host, int n, const long long** dev
 // sweep along `axis` of a view; see adsb_sweep_view
 int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view& vi,
                const long long* off_in_h, double* out, const adsb_view& vo, const long long* off_out_h,
-               bool managed = false) {
+               bool managed = false, const SweepFactor* Fsel = nullptr) {
     if (axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "sweep: bad axis");
     if (slot < 0 || slot >= ADSB_MAX_SLOTS || !c->ax[axis].fac[slot].set)
         return fail(ADSB_ESTATE, "sweep: no factor uploaded for this axis/slot");
-    const SweepFactor& F = c->ax[axis].fac[slot].f;
+    const SweepFactor& F = Fsel ? *Fsel : c->ax[axis].fac[slot].f;
     for (int d = 0; d < 3; ++d)
         if (vi.n[d] != vo.n[d]) return fail(ADSB_EINVAL, "sweep: in/out extents differ");
     if (vi.n[axis] != F.n) return fail(ADSB_EINVAL, "sweep: the view does not span the whole axis");
@@ -561,17 +596,13 @@ int adsb_set_axis_factor(adsb_ctx* c, int axis, int slot, int n, int kl, int ku,
     DevFactor& D = c->ax[axis].fac[slot];
     CU(cudaStreamSynchronize(c->stream));
     free_factor(D);
-    double *cfF, *cfB, *cfC, *T, *Rm, *W, *V;
-    int* pv;
-    if (int rc = upload_vec(P.cfF, 0, &cfF, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.cfB, 0, &cfB, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.cfC, 0, &cfC, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.pv, 0, &pv, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.T, 0, &T, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.Rm, 0, &Rm, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.W, 0, &W, &D.allocs)) return rc;
-    if (int rc = upload_vec(P.V, 0, &V, &D.allocs)) return rc;
-    D.f = SweepFactor{cfF, cfB, cfC, pv, T, Rm, W, V, P.n, P.ST, P.SC, P.KL, P.KD, P.piv, P.DF, P.DB, P.seq};
+    if (int rc = upload_plan(P, D.f, D.allocs)) return rc;
+    D.n = n;
+    D.kl = kl;
+    D.ku = ku;
+    D.ldab = ldab;
+    D.ab.assign(ab, ab + (size_t) ldab * n);
+    D.ipiv.assign(ipiv, ipiv + n);
     D.set = true;
     return ADSB_OK;
 }
@@ -599,6 +630,35 @@ int adsb_download(adsb_ctx* c, int b, double* host) {
         CU(cudaMemcpy2DAsync(host, c->cnt[0] * sizeof(double), c->buf[b], c->pitch0() * sizeof(double),
                              c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return ADSB_OK;
+}
+
+// Same copies without the trailing synchronise, on a caller-supplied stream (cudaStream_t as void*): lets a
+// caller overlap the upload of the next input and the download of the previous result with a step that runs
+// on the context's own stream.  The caller orders the streams (events) and keeps `host` pinned and alive.
+int adsb_upload_async(adsb_ctx* c, int b, const double* host, void* stream) {
+    if (!c || !host) return fail(ADSB_EINVAL, "upload_async: null argument");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, b)) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (c->pitch0() == c->cnt[0])
+        CU(cudaMemcpyAsync(c->buf[b], host, c->local_size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    else
+        CU(cudaMemcpy2DAsync(c->buf[b], c->pitch0() * sizeof(double), host, c->cnt[0] * sizeof(double),
+                             c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyHostToDevice, st));
+    return ADSB_OK;
+}
+
+int adsb_download_async(adsb_ctx* c, int b, double* host, void* stream) {
+    if (!c || !host) return fail(ADSB_EINVAL, "download_async: null argument");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "download_async: buffer not allocated");
+    if (int rc = select_device(c)) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (c->pitch0() == c->cnt[0])
+        CU(cudaMemcpyAsync(host, c->buf[b], c->local_size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    else
+        CU(cudaMemcpy2DAsync(host, c->cnt[0] * sizeof(double), c->buf[b], c->pitch0() * sizeof(double),
+                             c->cnt[0] * sizeof(double), c->rows(), cudaMemcpyDeviceToHost, st));
     return ADSB_OK;
 }
 
@@ -820,6 +880,184 @@ int adsb_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int
     put(Rm, P.Rm);
     put(W, P.W);
     put(V, P.V);
+    return ADSB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ segmented substitution
+namespace {
+
+int seg_of(adsb_ctx* c, int axis, int slot, SegSet** out) {
+    if (!c || axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "segments: bad axis");
+    if (slot < 0 || slot >= ADSB_MAX_SLOTS || !c->ax[axis].fac[slot].set)
+        return fail(ADSB_ESTATE, "segments: no factor uploaded for this axis/slot");
+    SegSet& g = c->ax[axis].fac[slot].seg;
+    if (!g.set) return fail(ADSB_ESTATE, "segments: adsb_set_axis_segments was not called for this axis/slot");
+    *out = &g;
+    return ADSB_OK;
+}
+
+// lines of a view perpendicular to `axis`: l0 = the other axis with the smaller stride
+int seg_geom(const adsb_ctx* c, int axis, const double* in, const adsb_view& vi, double* out, const adsb_view& vo,
+             int row_base, int s_lo, int s_hi, SegGeom& G) {
+    const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+    int l0 = (vi.s[a] <= vi.s[b]) ? a : b;
+    if (vi.n[l0] == 1 && vi.n[l0 == a ? b : a] > 1 && vi.s[axis] != 1) l0 = (l0 == a) ? b : a;
+    const int l1 = (l0 == a) ? b : a;
+    for (int d = 0; d < 3; ++d)
+        if (vi.n[d] != vo.n[d]) return fail(ADSB_EINVAL, "segments: in/out extents differ");
+    G = SegGeom{};
+    G.in = in;
+    G.out = out;
+    G.sj_in = vi.s[axis];
+    G.sj_out = vo.s[axis];
+    G.s0_in = vi.s[l0];
+    G.s0_out = vo.s[l0];
+    G.s1_in = vi.s[l1];
+    G.s1_out = vo.s[l1];
+    G.L0 = vi.n[l0];
+    G.L1 = vi.n[l1];
+    G.row_base = row_base;
+    G.s_lo = s_lo;
+    G.s_hi = s_hi;
+    if (G.L1 > 65535) return fail(ADSB_EINVAL, "segments: outer extent beyond grid limits");
+    (void) c;
+    return ADSB_OK;
+}
+
+int seg_check_rows(const SegSet& g, int s_lo, int s_hi, int row_base, int rows) {
+    if (s_lo < 0 || s_hi > g.dev.S || s_lo >= s_hi) return fail(ADSB_EINVAL, "segments: bad segment range");
+    if (g.bounds[s_lo] < row_base || g.bounds[s_hi] > row_base + rows)
+        return fail(ADSB_EINVAL, "segments: the view does not hold the rows of these segments");
+    return ADSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int adsb_set_axis_segments(adsb_ctx* c, int axis, int slot, int nseg, const int* bounds, int local_lo, int local_cnt) {
+    if (!c || axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "set_axis_segments: bad axis");
+    if (slot < 0 || slot >= ADSB_MAX_SLOTS || !c->ax[axis].fac[slot].set)
+        return fail(ADSB_ESTATE, "set_axis_segments: upload the factor first (adsb_set_axis_factor)");
+    if (!bounds || nseg < 1 || local_lo < 0 || local_cnt < 0 || local_lo + local_cnt > nseg)
+        return fail(ADSB_EINVAL, "set_axis_segments: bad segment arguments");
+    if (int rc = select_device(c)) return rc;
+    DevFactor& D = c->ax[axis].fac[slot];
+    SegPlan P;
+    if (int rc = build_segment_plan(D.n, D.kl, D.ku, D.ldab, D.ab.data(), D.ipiv.data(), nseg, bounds, 1e-20, P)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    free_segments(D.seg);
+    SegSet& g = D.seg;
+    int* d_bounds;
+    double *E, *Wf, *Vb, *XiF, *cf;
+    if (int rc = upload_vec(P.bounds, 0, &d_bounds, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.E, 0, &E, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.Wf, 0, &Wf, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.Vb, 0, &Vb, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.XiF, 0, &XiF, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.cf, 0, &cf, &g.allocs)) return rc;
+    g.dev = SegDev{P.n, P.KL, P.KD, P.S, P.DF, P.DB, d_bounds, E, Wf, Vb, XiF, cf};
+    g.bounds = P.bounds;
+    g.local_lo = local_lo;
+    g.local_cnt = local_cnt;
+    g.local.resize(local_cnt);
+    for (int i = 0; i < local_cnt; ++i) {
+        // pass-A factor of segment s: the factor's own columns [a, b), pivots renumbered
+        const int a = P.bounds[local_lo + i], b = P.bounds[local_lo + i + 1];
+        std::vector<int> ip(D.ipiv.begin() + a, D.ipiv.begin() + b);
+        for (int& v : ip) v -= a;
+        SweepPlan L;
+        if (int rc = build_sweep_plan(b - a, D.kl, D.ku, D.ldab, D.ab.data() + (size_t) a * D.ldab, ip.data(), SWEEP_CH, 1, L))
+            return rc;
+        if (int rc = upload_plan(L, g.local[i], g.allocs)) return rc;
+    }
+    g.set = true;
+    return ADSB_OK;
+}
+
+int adsb_segment_info(adsb_ctx* c, int axis, int slot, int* info8) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!info8) return fail(ADSB_EINVAL, "segment_info: null argument");
+    const int v[8] = {g->dev.KL, g->dev.KD, g->dev.DF, g->dev.DB, g->dev.S, g->local_lo, g->local_cnt, g->dev.n};
+    std::copy(v, v + 8, info8);
+    return ADSB_OK;
+}
+
+int adsb_seg_sweep_view(adsb_ctx* c, int axis, int slot, int seg, const double* in, const adsb_view* vin, double* out,
+                        const adsb_view* vout) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!in || !out || !vin || !vout) return fail(ADSB_EINVAL, "seg_sweep_view: null argument");
+    if (seg < g->local_lo || seg >= g->local_lo + g->local_cnt)
+        return fail(ADSB_EINVAL, "seg_sweep_view: segment is not local to this context");
+    if (int rc = select_device(c)) return rc;
+    return sweep_impl(c, axis, slot, in, *vin, nullptr, out, *vout, nullptr, false, &g->local[seg - g->local_lo]);
+}
+
+int adsb_seg_dseg_view(adsb_ctx* c, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
+                       const adsb_view* vin, double* const* dst, int ndst) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!xhat || !vin || !dst) return fail(ADSB_EINVAL, "seg_dseg_view: null argument");
+    if (int rc = seg_check_rows(*g, s_lo, s_hi, row_base, vin->n[axis])) return rc;
+    if (int rc = select_device(c)) return rc;
+    SegGeom G;
+    if (int rc = seg_geom(c, axis, xhat, *vin, nullptr, *vin, row_base, s_lo, s_hi, G)) return rc;
+    StageTimer t(c, 1 + axis);
+    cudaError_t e = (cudaError_t) launch_seg_dseg(g->dev, G, dst, ndst, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "seg_dseg kernel");
+    c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_seg_din_view(adsb_ctx* c, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
+                      const adsb_view* vin, const double* dseg, double* din, double* const* xdst, int ndst) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!xhat || !vin || !dseg || !din || !xdst) return fail(ADSB_EINVAL, "seg_din_view: null argument");
+    if (int rc = seg_check_rows(*g, s_lo, s_hi, row_base, vin->n[axis])) return rc;
+    if (int rc = select_device(c)) return rc;
+    SegGeom G;
+    if (int rc = seg_geom(c, axis, xhat, *vin, nullptr, *vin, row_base, s_lo, s_hi, G)) return rc;
+    StageTimer t(c, 1 + axis);
+    cudaError_t e = (cudaError_t) launch_seg_din(g->dev, G, dseg, din, xdst, ndst, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "seg_din kernel");
+    c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_seg_tin(adsb_ctx* c, int axis, int slot, int s_lo, int s_hi, long long lines, const double* X, double* tin) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!X || !tin || lines < 1 || s_lo < 0 || s_hi > g->dev.S || s_lo >= s_hi)
+        return fail(ADSB_EINVAL, "seg_tin: bad argument");
+    if (int rc = select_device(c)) return rc;
+    StageTimer t(c, 1 + axis);
+    cudaError_t e = (cudaError_t) launch_seg_tin(g->dev, s_lo, s_hi, lines, X, tin, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "seg_tin kernel");
+    c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_seg_correct_view(adsb_ctx* c, int axis, int slot, int s_lo, int s_hi, int row_base, const double* in,
+                          const adsb_view* vin, double* out, const adsb_view* vout, const double* din,
+                          const double* tin_or_x) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!in || !out || !vin || !vout || !din || !tin_or_x) return fail(ADSB_EINVAL, "seg_correct_view: null argument");
+    if (int rc = seg_check_rows(*g, s_lo, s_hi, row_base, vin->n[axis])) return rc;
+    if (int rc = select_device(c)) return rc;
+    SegGeom G;
+    if (int rc = seg_geom(c, axis, in, *vin, out, *vout, row_base, s_lo, s_hi, G)) return rc;
+    int max_rows = 0;
+    for (int s = s_lo; s < s_hi; ++s) max_rows = std::max(max_rows, g->bounds[s + 1] - g->bounds[s]);
+    StageTimer t(c, 1 + axis);
+    cudaError_t e = (cudaError_t) launch_seg_correct(g->dev, G, din, tin_or_x, g->dev.DB == 1 ? 1 : 0, max_rows, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "seg_correct kernel");
+    c->launches++;
     return ADSB_OK;
 }
 

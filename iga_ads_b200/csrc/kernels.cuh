@@ -140,6 +140,34 @@ int launch_rhs_quadrature(int ndim, const QuadAxes& A, const RhsGeom& g, int sou
 int launch_zero_box(double* y, const int n[3], const long long s[3], cudaStream_t st);
 int launch_axpy_box(double* y, const double* x, double a, const int n[3], const long long s[3], cudaStream_t st);
 
+// ---- segmented substitution (kernels_seg.cu; tables: build_segment_plan in host_setup.cpp)
+struct SegDev {
+    int n, KL, KD, S, DF, DB;
+    const int* bounds;   // [S+1]
+    const double* E;     // [S][KL][KL]
+    const double* Wf;    // [S][DF][KL][KL]
+    const double* Vb;    // [S][DB][KD][KD]
+    const double* XiF;   // [S][KD][KL]
+    const double* cf;    // [n][KD+KL]  Psi | Xi
+};
+// Lines of a view: element (row j, line (l0, l1)) at (j - row_base)*sj + l0*s0 + l1*s1; state arrays are
+// [S][K][L0*L1] with line = l0 + L0*l1.  row_base: global row of the view's first row (a slab's first plane).
+struct SegGeom {
+    const double* in;
+    double* out;
+    long long sj_in, sj_out, s0_in, s0_out, s1_in, s1_out;
+    int L0, L1;
+    int row_base;
+    int s_lo, s_hi;  // segments [s_lo, s_hi)
+};
+int launch_seg_dseg(const SegDev& T, const SegGeom& G, double* const* dst, int ndst, cudaStream_t st);
+int launch_seg_din(const SegDev& T, const SegGeom& G, const double* dseg, double* din, double* const* xdst, int ndst,
+                   cudaStream_t st);
+int launch_seg_tin(const SegDev& T, int s_lo, int s_hi, long long L, const double* X, double* tin, cudaStream_t st);
+// max_rows: longest segment among [s_lo, s_hi); tin_is_x: chain depth 1, `tin` is the X array itself
+int launch_seg_correct(const SegDev& T, const SegGeom& G, const double* din, const double* tin, int tin_is_x,
+                       int max_rows, cudaStream_t st);
+
 // vnx > 0: `values` are the first elements of a tensor with x rows of vnx doubles, vpitch apart (else dense)
 int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,
                      const double* values, cudaStream_t st, int vnx = 0, long long vpitch = 0);

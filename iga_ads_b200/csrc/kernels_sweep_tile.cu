@@ -325,14 +325,29 @@ bool encode_tensor_map3(void* map, const double* base, const unsigned long long 
 // caller then uses the register-path kernel), or a CUDA error.
 int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
                       const long long* off_out_h, cudaStream_t st) {
-    // lines per tile: 16 (8 lanes x 2 lines x <= 29 chunks = one CTA); short lines (<= 16 chunks, n <= 288)
-    // take 32 so the CTA still has ~8 warps and the strided tiles move 256 B rows.  ADSB_SWEEP_NL=12|16|32 pins it.
+    // lines per tile: as many lanes as keep the CTA near 256 consumer threads (lanes x chunks): 16 lines for
+    // 17..32 chunks (n <= 576), 32 for 9..16, 64 for 5..8, 128 for <= 4 chunks (the thin slabs of a sharded z
+    // sweep); wider tiles also move longer rows (128 B .. 1 KB).  ADSB_SWEEP_NL=12|16|32|64|128 pins it.
     static const int NL_env = [] {
         const char* e = getenv("ADSB_SWEEP_NL");
         const int v = e ? atoi(e) : 0;
-        return (v == 12 || v == 16 || v == 32) ? v : 0;
+        return (v == 12 || v == 16 || v == 32 || v == 64 || v == 128) ? v : 0;
     }();
-    const int NL = NL_env ? NL_env : (F.SC * 16 <= 256 ? 32 : 16);
+    int NL = NL_env;
+    if (!NL) {
+        // shared memory of a CTA with nl lines per tile and two ring slots (same arithmetic as below)
+        auto fits = [&](int nl) {
+            const size_t rows = (size_t) F.SC * SWEEP_CH + F.KL + F.KD;
+            const size_t fixed = ((size_t) F.SC * (F.KL + F.KD) * nl +
+                                  rows * (sweep_pitch(F.KL) + sweep_pitch(F.KD + 1) + sweep_pitch(F.KD + F.KL)) +
+                                  (size_t) F.SC * (F.KL * F.KL + F.KD * F.KD) * SWEEP_MAX_DEPTH_DEV) * 8 + 256;
+            const size_t tile = ((size_t) F.SC * SWEEP_CH + F.KL + 18) * nl * 8;
+            return fixed + 2 * tile <= 226 * 1024;
+        };
+        NL = 16;
+        const int cap = contig ? 32 : 128;  // whole lines per tile: more of them only costs shared memory
+        while (NL < cap && NL * F.SC <= 256 && fits(2 * NL)) NL *= 2;
+    }
     const int NLt = NL / SWEEP_RL;
     if (contig && (off_in_h || off_out_h)) return -1;
     const int ncons = (NLt * F.SC + 31) / 32 * 32;
@@ -415,7 +430,9 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
     T.nbuf = nbuf;
     const size_t smem = (size_t) nbuf * T.tile_doubles * 8 + fixed_bytes;
     tile_kern_t k = NL == 12 ? pick<12>(F.KL, F.piv != 0, contig)
-                    : NL == 32 ? pick<32>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
+                    : NL == 32 ? pick<32>(F.KL, F.piv != 0, contig)
+                    : NL == 64 ? pick<64>(F.KL, F.piv != 0, contig)
+                    : NL == 128 ? pick<128>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
     if (!k) return -1;
     cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;

@@ -31,9 +31,21 @@ public:
 
     adsb_ctx* handle() const { return h_; }
 
+    // managed buffer ids are recycled: a tensor returns its id when it is destroyed or re-shaped
     int new_buffer() {
+        if (!free_bufs_.empty()) {
+            const int b = free_bufs_.back();
+            free_bufs_.pop_back();
+            return b;
+        }
         if (next_buf_ >= ADSB_MAX_BUFFERS) throw std::runtime_error("libadsb200: out of managed buffers");
         return next_buf_++;
+    }
+    void free_buffer(int b) noexcept {
+        try {
+            free_bufs_.push_back(b);
+        } catch (...) {  // out of memory while recycling an id: leak the id, never throw from a destructor
+        }
     }
 
     // slot holding this factor on `axis`, uploading it first if its content is new
@@ -62,6 +74,7 @@ public:
 private:
     adsb_ctx* h_ = nullptr;
     int next_buf_ = 0;
+    std::vector<int> free_bufs_;
     std::array<std::vector<std::uint64_t>, 3> slots_;
     std::array<int, 3> evict_{};
 };

@@ -22,6 +22,37 @@ public:
 
     explicit tensor(const size_array& sizes) : sizes_{sizes}, data_(count(sizes)) { }
 
+    // Value semantics of the reference tensor (a plain std::vector owner): a copy holds the source's CURRENT
+    // values -- downloaded first when the device copy is the newer one -- and starts without a device mirror
+    // (the mirror's managed buffer belongs to the source alone).  Moves carry the mirror along, so
+    // std::swap(u, u_prev) keeps both tensors resident.
+    tensor(const tensor& o) : sizes_{o.sizes_}, data_(o.host_data()) { }
+    tensor& operator=(const tensor& o) {
+        if (this != &o) {
+            const bool same_shape = sizes_ == o.sizes_;
+            data_ = o.host_data();
+            sizes_ = o.sizes_;
+            if (!same_shape) release();  // the managed buffer was sized for the old shape
+            m_.host_valid = true;        // an attached destination stays attached; its device copy is stale now
+            m_.dev_valid = false;
+        }
+        return *this;
+    }
+    tensor(tensor&& o) noexcept : sizes_{o.sizes_}, data_(std::move(o.data_)), m_(std::move(o.m_)) {
+        o.m_ = device::mirror{};
+    }
+    tensor& operator=(tensor&& o) noexcept {
+        if (this != &o) {
+            release();
+            sizes_ = o.sizes_;
+            data_ = std::move(o.data_);
+            m_ = std::move(o.m_);
+            o.m_ = device::mirror{};
+        }
+        return *this;
+    }
+    ~tensor() { release(); }
+
     int size() const { return static_cast<int>(data_.size()); }
     int size(int dim) const { return sizes_[dim]; }
     const size_array& sizes() const { return sizes_; }
@@ -75,6 +106,14 @@ public:
     }
 
 private:
+    const std::vector<T>& host_data() const {
+        host_for_read();
+        return data_;
+    }
+    void release() noexcept {  // hand the managed buffer id back to the context
+        if (m_.buf >= 0 && m_.ctx) m_.ctx->free_buffer(m_.buf);
+        m_ = device::mirror{};
+    }
     static std::size_t count(const size_array& s) {
         std::size_t n = 1;
         for (int v : s) n *= static_cast<std::size_t>(v);

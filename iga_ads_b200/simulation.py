@@ -85,6 +85,13 @@ class Context:
         check(self.lib.adsb_download(self.h, buf, d_(out)))
         return out
 
+    def upload_async(self, buf, host_ptr, stream_ptr):
+        """host_ptr: pinned host memory holding local_size doubles; enqueued on the given CUDA stream"""
+        check(self.lib.adsb_upload_async(self.h, buf, ctypes.c_void_p(host_ptr), ctypes.c_void_p(stream_ptr)))
+
+    def download_async(self, buf, host_ptr, stream_ptr):
+        check(self.lib.adsb_download_async(self.h, buf, ctypes.c_void_p(host_ptr), ctypes.c_void_p(stream_ptr)))
+
     def swap(self, a, b):
         check(self.lib.adsb_swap(self.h, a, b))
 
@@ -140,6 +147,45 @@ class Context:
         check(self.lib.adsb_rhs_view(self.h, ctypes.byref(form), ctypes.c_void_p(in_ptr), ctypes.byref(vin),
                                      i_(il), ctypes.c_void_p(forcing_ptr) if forcing_ptr else None,
                                      ctypes.c_void_p(out_ptr), ctypes.byref(vout), i_(ol)))
+
+    # ---- segmented substitution (long lines, slab-sharded sweeps); see include/adsb200.h
+    def set_segments(self, axis, slot, bounds, local_lo=0, local_cnt=None):
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        nseg = len(b) - 1
+        check(self.lib.adsb_set_axis_segments(self.h, axis, slot, nseg, i_(b), local_lo,
+                                              nseg - local_lo if local_cnt is None else local_cnt))
+
+    def segment_info(self, axis, slot):
+        v = np.zeros(8, dtype=np.int32)
+        check(self.lib.adsb_segment_info(self.h, axis, slot, i_(v)))
+        return dict(zip(("KL", "KD", "DF", "DB", "S", "local_lo", "local_cnt", "n"), (int(x) for x in v)))
+
+    def seg_sweep_view(self, axis, slot, seg, in_ptr, vin, out_ptr, vout):
+        check(self.lib.adsb_seg_sweep_view(self.h, axis, slot, seg, ctypes.c_void_p(in_ptr), ctypes.byref(vin),
+                                           ctypes.c_void_p(out_ptr), ctypes.byref(vout)))
+
+    @staticmethod
+    def _ptr_list(ptrs):
+        return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs]), len(ptrs)
+
+    def seg_dseg_view(self, axis, slot, s_lo, s_hi, row_base, xhat_ptr, vin, dst_ptrs):
+        arr, n = self._ptr_list(dst_ptrs)
+        check(self.lib.adsb_seg_dseg_view(self.h, axis, slot, s_lo, s_hi, row_base, ctypes.c_void_p(xhat_ptr),
+                                          ctypes.byref(vin), arr, n))
+
+    def seg_din_view(self, axis, slot, s_lo, s_hi, row_base, xhat_ptr, vin, dseg_ptr, din_ptr, x_dst_ptrs):
+        arr, n = self._ptr_list(x_dst_ptrs)
+        check(self.lib.adsb_seg_din_view(self.h, axis, slot, s_lo, s_hi, row_base, ctypes.c_void_p(xhat_ptr),
+                                         ctypes.byref(vin), ctypes.c_void_p(dseg_ptr), ctypes.c_void_p(din_ptr), arr, n))
+
+    def seg_tin(self, axis, slot, s_lo, s_hi, lines, x_ptr, tin_ptr):
+        check(self.lib.adsb_seg_tin(self.h, axis, slot, s_lo, s_hi, lines, ctypes.c_void_p(x_ptr),
+                                    ctypes.c_void_p(tin_ptr)))
+
+    def seg_correct_view(self, axis, slot, s_lo, s_hi, row_base, in_ptr, vin, out_ptr, vout, din_ptr, tin_or_x_ptr):
+        check(self.lib.adsb_seg_correct_view(self.h, axis, slot, s_lo, s_hi, row_base, ctypes.c_void_p(in_ptr),
+                                             ctypes.byref(vin), ctypes.c_void_p(out_ptr), ctypes.byref(vout),
+                                             ctypes.c_void_p(din_ptr), ctypes.c_void_p(tin_or_x_ptr)))
 
     # ---- measurement
     def enable_timing(self, on=True):

@@ -1,0 +1,413 @@
+"""Multi-GPU ADS step on z-slabs with a DISTRIBUTED z substitution: nothing is transposed.
+
+One process per GPU.  Rank r owns the planes [bounds[r], bounds[r+1]) of the canonical (x fastest)
+tensor.  Per sub-step (same sequence as simulation.py / adsb_step):
+
+    right-hand side on the slab (p halo planes of u_prev from the two neighbours)
+    x sweep, y sweep                               slab-local
+    z sweep = segmented substitution, the slab being one segment of every z line:
+        pass A   the slab's own columns of the factor, zero incoming states    (local sweep kernel)
+        dseg     KL forward boundary values per line  -> stored into the next ranks' state arrays
+        din / X  KD backward boundary values per line -> stored into the previous ranks' state arrays
+        pass B   x = xhat + Xi din + Psi tin          -> interior of the next state buffer
+    boundary planes of the new state -> the neighbours' halo regions
+
+Only KL + KD doubles per z line and rank boundary cross NVLink (8.4 MB per rank at 514^2 lines, p = 2)
+instead of the 119 MB of a slab-to-slab transpose; the price is pass B, one more streaming pass over the
+slab.  The state arrays and the halo'ed state buffers live in symmetric memory
+(torch.distributed._symmetric_memory): kernels and copy engines store straight through peer pointers,
+three signal-pad barriers per sub-step order them.  See iga_ads_b200/sharded.py for the transposing
+variant (kept for factors whose segments cannot be cut: growing boundary responses).
+
+`SlabSim` is one rank; `VirtualCluster` runs several ranks in lockstep on ONE device (same kernels,
+same pointer plumbing, peers are plain tensors) -- that is how the path is tested on a single GPU.
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import Form, View
+from .host import segment_bounds
+from .simulation import FORCING, PROBLEMS, Context, timesteps_config
+
+
+class _LocalPeers:
+    """Peer access for virtual ranks on one device: every rank's arrays are ordinary tensors."""
+
+    def __init__(self):
+        self.ranks = []
+
+    def ptr(self, rank, name):
+        return self.ranks[rank].sym[name].data_ptr()
+
+    def tensor(self, rank, name):
+        return self.ranks[rank].sym[name]
+
+    def barrier(self, channel):
+        pass  # lockstep execution (VirtualCluster) orders the phases
+
+
+class _SelfPeers(_LocalPeers):
+    """Timing vehicle: one rank of a `world`-rank run alone on a device; every peer store lands in the rank's
+    own arrays (results are meaningless, the work per kernel is that of a real rank)."""
+
+    def ptr(self, rank, name):
+        return self.ranks[0].sym[name].data_ptr()
+
+    def tensor(self, rank, name):
+        return self.ranks[0].sym[name]
+
+
+class _SymmPeers:
+    """Peer access through one symmetric allocation per rank: [array 0 | array 1 | ...] in a fixed order."""
+
+    def __init__(self, sim, sizes):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.sim, self.torch = sim, torch
+        self.offsets, off = {}, 0
+        for name, count in sizes:
+            self.offsets[name] = (off, count)
+            off += count + (count & 1)
+        self.buf = symm.empty(off, dtype=torch.float64, device=sim.dev)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.base = [int(v) for v in self.hdl.buffer_ptrs]
+        self.total = off
+        self.hdl.barrier(channel=0)
+
+    def local(self, name):
+        o, c = self.offsets[name]
+        return self.buf[o:o + c]
+
+    def ptr(self, rank, name):
+        return self.base[rank] + 8 * self.offsets[name][0]
+
+    def tensor(self, rank, name):
+        o, c = self.offsets[name]
+        return self.hdl.get_buffer(rank, (c,), self.torch.float64, o)
+
+    def barrier(self, channel):
+        self.hdl.barrier(channel=channel)
+
+
+class SlabSim:
+    """One rank of a z-slab sharded run of a 3-D problem of simulation.PROBLEMS."""
+
+    def __init__(self, problem, p, elements, dt, rank, world, device, peers=None, steps=1):
+        import torch
+
+        self.torch = torch
+        self.rank, self.world, self.p, self.dt = int(rank), int(world), int(p), float(dt)
+        self.dev = torch.device("cuda", device)
+        cls = PROBLEMS[problem] if isinstance(problem, str) else problem
+        # the single-GPU problem object supplies dimensions, matrices and the sub-step program; its own
+        # device context is never created
+        self.model = cls(p, elements, timesteps_config(steps, dt), device=device)
+        self.dims = self.model.dims
+        if len(self.dims) != 3:
+            raise ValueError("slab sharding is for the 3-D problems")
+        self.n = tuple(d.dofs() for d in self.dims)
+        nx, ny, nz = self.n
+        self.pitch = nx + (nx & 1)           # x rows padded to 16 B (TMA), as the managed tensors are
+        self.plane = ny * self.pitch         # doubles per z plane
+        self.lines = nx * ny                 # z lines; state arrays are [S][K][lines], line = x + nx*y
+        # ---- factors: let the model factorise exactly as on one GPU, but capture instead of uploading
+        self.factors = {}
+
+        class _Capture:
+            def __init__(s, ndim):
+                s.ndim = ndim
+
+            def set_axis(s, ax, dim):
+                pass
+
+            def set_factor(s, ax, slot, lu, ipiv, kl, ku):
+                self.factors[ax, slot] = (np.array(lu), np.array(ipiv), kl, ku)
+
+            def upload(s, *a):
+                pass
+
+            def load_tensor(s, *a):
+                s.want_forcing = a
+
+            local_size = 0
+
+        cap = _Capture(3)
+        self.model.ctx = cap
+        self.model.prepare_matrices()
+        self.model.ctx = None
+        self.substeps = self.model.substeps()
+        self.zslots = sorted({int(s.slots[2]) for s in self.substeps})
+        # ---- slabs = segments of the z lines; cuts must be free of row interchanges for every z factor
+        lu0, ipiv0, kl, ku = self.factors[2, self.zslots[0]]
+        self.bounds = segment_bounds(ipiv0, kl, world, 1) if world > 1 else np.array([0, nz], dtype=np.int32)
+        self.z0, self.cz = int(self.bounds[rank]), int(self.bounds[rank + 1] - self.bounds[rank])
+        if self.cz < max(p, 1):
+            raise ValueError("slabs thinner than the spline degree are not supported")
+        self.ctx = Context(self.n, lo=(0, 0, self.z0), cnt=(nx, ny, self.cz), device=device)
+        self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        for ax, d in enumerate(self.dims):
+            self.ctx.set_axis(ax, d)
+        for (ax, slot), (lu, ipiv, fkl, fku) in self.factors.items():
+            self.ctx.set_factor(ax, slot, lu, ipiv, fkl, fku)
+        self.seg = {}
+        for slot in self.zslots:
+            self.ctx.set_segments(2, slot, self.bounds, rank, 1)   # raises when the factor cannot be cut
+            self.seg[slot] = self.ctx.segment_info(2, slot)
+        KL = max(s["KL"] for s in self.seg.values())
+        KD = max(s["KD"] for s in self.seg.values())
+        self.KL, self.KD = KL, KD
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        S = world
+        nhalo = (max(np.diff(self.bounds)) + 2 * p) * self.plane
+        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines)]
+        if peers is None and world > 1:
+            peers = _SymmPeers(self, sizes)
+            self.sym = {name: peers.local(name) for name, _ in sizes}
+        else:
+            self.sym = {name: torch.zeros(count, **f64) for name, count in sizes}
+            if peers is None:
+                peers = _LocalPeers()
+            peers.ranks.append(self)
+        self.peers = peers
+        self.work = torch.zeros(self.cz * self.plane, **f64)
+        self.din = torch.zeros(S * KL * self.lines, **f64)
+        self.tin = torch.zeros(S * KD * self.lines, **f64) if any(s["DB"] > 1 for s in self.seg.values()) else None
+        self.forcing = None
+        if any(float(s.form.gamma) != 0.0 for s in self.substeps):
+            self.ctx.load_tensor(1, False, FORCING)          # slab of the load tensor (context lo / cnt)
+            self.forcing = self.ctx.device_ptr(FORCING)
+        self.cur = 0
+        self.launches = 0
+        self.exchange_bytes = 0
+        self.timing, self._marks = False, []
+        self.graph = None
+
+    # ---- geometry helpers
+    def _view(self, planes):
+        return View.make([self.n[0], self.n[1], planes], [1, self.pitch, self.plane])
+
+    def halo(self, k):
+        return self.sym["h1" if k else "h0"]
+
+    def interior(self, k):
+        return self.halo(k)[self.p * self.plane:(self.p + self.cz) * self.plane]
+
+    def set_local_state(self, host):
+        """host: this rank's slab [cz][ny][nx] (dense); call on every rank, then `publish()`"""
+        t = self.torch
+        src = t.as_tensor(np.ascontiguousarray(host, dtype=np.float64).reshape(self.cz, self.n[1], self.n[0]))
+        dst = self.interior(self.cur).view(self.cz, self.n[1], self.pitch)
+        dst[:, :, :self.n[0]].copy_(src, non_blocking=True)
+
+    def local_state(self):
+        """(z0, array [cz][ny][nx])"""
+        a = self.interior(self.cur).view(self.cz, self.n[1], self.pitch)[:, :, :self.n[0]]
+        return self.z0, a.cpu().numpy()
+
+    def _mark(self, name):
+        if self.timing:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def phase_times(self):
+        self.torch.cuda.synchronize()
+        out = {}
+        for (_, e0), (n1, e1) in zip(self._marks[:-1], self._marks[1:]):
+            if n1 != "begin":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._marks = []
+        return out
+
+    # ---- the phases of one sub-step; between two phases every rank must have finished the earlier one
+    def phase_publish(self, k):
+        """boundary planes of state buffer k -> the neighbours' halo regions (copy engines)"""
+        p, pl, r = self.p, self.plane, self.rank
+        if p == 0 or self.world == 1:
+            return
+        name = "h1" if k else "h0"
+        mine = self.halo(k)
+        if r > 0:   # my first p planes are the upper halo of rank r-1
+            cn = int(self.bounds[r] - self.bounds[r - 1])
+            dst = self.peers.tensor(r - 1, name)[(p + cn) * pl:(2 * p + cn) * pl]
+            dst.copy_(mine[p * pl:2 * p * pl], non_blocking=True)
+            self.exchange_bytes += 8 * p * pl
+        if r < self.world - 1:   # my last p planes are the lower halo of rank r+1
+            dst = self.peers.tensor(r + 1, name)[0:p * pl]
+            dst.copy_(mine[self.cz * pl:(self.cz + p) * pl], non_blocking=True)
+            self.exchange_bytes += 8 * p * pl
+
+    def phase_local(self, sub):
+        """right-hand side, x and y sweeps, pass A of the z sweep, forward boundary values"""
+        p, pl, nz = self.p, self.plane, self.n[2]
+        H = self.halo(self.cur)
+        lo, hi = max(0, self.z0 - p), min(nz, self.z0 + self.cz + p)
+        in_ptr = H.data_ptr() + 8 * (lo - self.z0 + p) * pl
+        wk = self.work.data_ptr()
+        v = self._view(self.cz)
+        self._mark("begin")
+        self.ctx.rhs_view(sub.form, in_ptr, self._view(hi - lo), [0, 0, lo], wk, v, [0, 0, self.z0],
+                          forcing_ptr=self.forcing if float(sub.form.gamma) != 0.0 else None)
+        self._mark("rhs")
+        self.ctx.sweep_view(0, int(sub.slots[0]), wk, v, wk, v)
+        self._mark("sweep_x")
+        self.ctx.sweep_view(1, int(sub.slots[1]), wk, v, wk, v)
+        self._mark("sweep_y")
+        slot = int(sub.slots[2])
+        if self.world == 1:
+            self.ctx.sweep_view(2, slot, wk, v, wk, v)
+            self.launches += 4
+            self._mark("sweep_z")
+            return
+        self.ctx.seg_sweep_view(2, slot, self.rank, wk, v, wk, v)
+        self._mark("sweep_z_a")
+        DF = self.seg[slot]["DF"]
+        dst = [self.peers.ptr(q, "dseg") for q in range(self.rank + 1, min(self.world, self.rank + DF + 1))]
+        if dst:
+            self.ctx.seg_dseg_view(2, slot, self.rank, self.rank + 1, self.z0, wk, v, dst)
+            self.exchange_bytes += 8 * self.seg[slot]["KL"] * self.lines * len(dst)
+            self.launches += 1
+        self.launches += 4
+        self._mark("dseg")
+
+    def phase_backward(self, sub):
+        """din from the previous ranks' forward values; backward boundary values to the previous ranks"""
+        if self.world == 1:
+            return
+        slot = int(sub.slots[2])
+        DB = self.seg[slot]["DB"]
+        dst = [self.sym["x"].data_ptr()] + [self.peers.ptr(q, "x") for q in range(max(0, self.rank - DB), self.rank)]
+        self.ctx.seg_din_view(2, slot, self.rank, self.rank + 1, self.z0, self.work.data_ptr(), self._view(self.cz),
+                              self.sym["dseg"].data_ptr(), self.din.data_ptr(), dst)
+        self.exchange_bytes += 8 * self.seg[slot]["KD"] * self.lines * (len(dst) - 1)
+        self.launches += 1
+        self._mark("din")
+
+    def phase_correct(self, sub):
+        """pass B into the interior of the other state buffer; swap; publish the new boundary planes"""
+        nxt = 1 - self.cur
+        out_ptr = self.interior(nxt).data_ptr()
+        v = self._view(self.cz)
+        if self.world == 1:
+            self.interior(nxt).copy_(self.work, non_blocking=True)
+        else:
+            slot = int(sub.slots[2])
+            tin = self.sym["x"]
+            if self.seg[slot]["DB"] > 1:
+                self.ctx.seg_tin(2, slot, self.rank, self.rank + 1, self.lines, self.sym["x"].data_ptr(), self.tin.data_ptr())
+                tin = self.tin
+                self.launches += 1
+            self.ctx.seg_correct_view(2, slot, self.rank, self.rank + 1, self.z0, self.work.data_ptr(), v, out_ptr, v,
+                                      self.din.data_ptr(), tin.data_ptr())
+            self.launches += 1
+        self._mark("correct")
+        self.cur = nxt
+        self.phase_publish(self.cur)
+        self._mark("halo")
+
+    PHASES = ("phase_local", "phase_backward", "phase_correct")
+
+    # ---- one rank of a real multi-GPU run
+    def publish(self):
+        self.peers.barrier(0)
+        self.phase_publish(self.cur)
+        self.peers.barrier(1)
+
+    def step(self):
+        for sub in self.substeps:
+            self.phase_local(sub)
+            self.peers.barrier(0)
+            self._mark("barrier")
+            self.phase_backward(sub)
+            self.peers.barrier(1)
+            self._mark("barrier")
+            self.phase_correct(sub)
+            self.peers.barrier(2)
+            self._mark("barrier")
+
+    def advance(self, nsteps, graph=None):
+        """nsteps steps; with graph=True (default on > 1 GPU, ADSB_SLAB_GRAPH=0 disables) one step is captured
+        into a CUDA graph after two eager steps and replayed (the state buffers alternate, so a graph holds
+        two steps)."""
+        use_graph = (self.world > 1 and os.environ.get("ADSB_SLAB_GRAPH", "1") != "0") if graph is None else graph
+        n = int(nsteps)
+        while n > 0:
+            if use_graph and n >= 2 and self.cur == 0 and not self.timing and getattr(self, "_eager", 0) >= 2:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+                self.launches += self._graph_delta[0]
+                self.exchange_bytes += self._graph_delta[1]
+                n -= 2
+            else:
+                self.step()
+                self._eager = getattr(self, "_eager", 0) + 1
+                n -= 1
+
+    def _capture(self):
+        torch = self.torch
+        main = torch.cuda.current_stream(self.dev)
+        l0, b0 = self.launches, self.exchange_bytes
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+            self.step()
+            self.step()
+        self.ctx.set_stream(main.cuda_stream)
+        self._graph_delta = (self.launches - l0, self.exchange_bytes - b0)
+        self.launches, self.exchange_bytes = l0, b0
+        self.graph = g
+
+
+class VirtualCluster:
+    """`world` ranks of SlabSim on ONE device, run in lockstep (phase by phase): the single-GPU test vehicle
+    of the distributed path.  Peer stores land in ordinary tensors of the same process."""
+
+    def __init__(self, problem, p, elements, dt, world, device=0):
+        self.peers = _LocalPeers()
+        self.ranks = [SlabSim(problem, p, elements, dt, r, world, device, peers=self.peers) for r in range(world)]
+        self.n = self.ranks[0].n
+
+    def set_state(self, full):
+        nx, ny, nz = self.n
+        a = np.asarray(full).reshape(nz, ny, nx)
+        for s in self.ranks:
+            s.set_local_state(a[s.z0:s.z0 + s.cz])
+        for s in self.ranks:
+            s.phase_publish(s.cur)
+
+    def state(self):
+        nx, ny, nz = self.n
+        out = np.zeros((nz, ny, nx))
+        for s in self.ranks:
+            z0, a = s.local_state()
+            out[z0:z0 + a.shape[0]] = a
+        return out.ravel()
+
+    def step(self, nsteps=1):
+        for _ in range(nsteps):
+            for i in range(len(self.ranks[0].substeps)):
+                for phase in SlabSim.PHASES:
+                    for s in self.ranks:
+                        getattr(s, phase)(s.substeps[i])
+        self.ranks[0].torch.cuda.synchronize()
+
+
+def gather_state(sim):
+    """All ranks: the full tensor [z][y][x] on every rank (test helper; host memory)."""
+    import torch.distributed as dist
+
+    z0, arr = sim.local_state()
+    pieces = [None] * sim.world
+    dist.all_gather_object(pieces, (z0, arr))
+    nx, ny, nz = sim.n
+    full = np.zeros((nz, ny, nx))
+    for z, a in pieces:
+        full[z:z + a.shape[0]] = a
+    return full

@@ -121,6 +121,11 @@ int adsb_set_axis_factor(adsb_ctx* ctx, int axis, int slot, int n, int kl, int k
  * Device mirrors of lin::tensor objects (include/ads/lin/tensor/tensor.hpp:14-50). */
 int adsb_upload(adsb_ctx* ctx, int buf, const double* host);
 int adsb_download(adsb_ctx* ctx, int buf, double* host);
+/* The same copies enqueued on `cuda_stream` (cudaStream_t as void*) without waiting: pinned `host` memory,
+ * the caller orders the stream against the context's own (events) -- used to overlap the next input's
+ * upload and the previous result's download with a running step.  The first use of a buffer allocates it. */
+int adsb_upload_async(adsb_ctx* ctx, int buf, const double* host, void* cuda_stream);
+int adsb_download_async(adsb_ctx* ctx, int buf, double* host, void* cuda_stream);
 int adsb_swap(adsb_ctx* ctx, int buf_a, int buf_b);        /* std::swap(u, u_prev) */
 int adsb_zero(adsb_ctx* ctx, int buf);                      /* zero(rhs), tensor.hpp:44-50 */
 int adsb_bind(adsb_ctx* ctx, int buf, double* device_ptr);  /* adopt caller-owned device memory */
@@ -247,6 +252,35 @@ int adsb_segment_bounds(int n, int kl, const int* ipiv, int nseg, int align, int
  * cf[n*(KD+KL)] (Psi | Xi per row); any output may be NULL.  tol <= 0: default chain cut-off 1e-20. */
 int adsb_segment_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int nseg, const int* bounds,
                       double tol, int* dims, double* E, double* Wf, double* Vb, double* XiF, double* cf);
+
+/* Cut the factor already uploaded to (axis, slot) into nseg segments; builds and uploads the segment tables
+ * and the pass-A factors of segments [local_lo, local_lo + local_cnt) (a sharded rank: its own slab only).
+ * Fails with ADSB_EINVAL when a cut crosses a row interchange, a segment is shorter than the band, or the
+ * factor's boundary responses grow (then use the unsegmented sweep / the transposing exchange). */
+int adsb_set_axis_segments(adsb_ctx* ctx, int axis, int slot, int nseg, const int* bounds, int local_lo, int local_cnt);
+/* info8 = {KL, KD, DF, DB, S, local_lo, local_cnt, n}: state widths (doubles per line and segment boundary:
+ * KL forward, KD backward) and chain depths (how many segments to the left / right a segment depends on). */
+int adsb_segment_info(adsb_ctx* ctx, int axis, int slot, int* info8);
+
+/* Pass A: dgbtrs of segment `seg` alone; the view spans exactly the rows of that segment along `axis`. */
+int adsb_seg_sweep_view(adsb_ctx* ctx, int axis, int slot, int seg, const double* in, const adsb_view* vin, double* out,
+                        const adsb_view* vout);
+/* Boundary states.  The view holds the rows [row_base, row_base + vin->n[axis]) of the line (all of it on one
+ * GPU; a rank's slab in a sharded run).  State arrays are [S][K][lines] doubles, lines = product of the two
+ * other extents (lower-stride axis fastest); dst / xdst list every array the values are stored to -- the
+ * local one and, through peer pointers, those of the ranks that depend on this segment.
+ *   dseg:  Dseg[s] = E_s * xhat_s[last KL rows]                                   s in [s_lo, s_hi)
+ *   din:   din[s] = sum_{d=1..DF} Wf[s][d] Dseg[s-d];  X[s] = xhat_s[first KD rows] + XiF_s din[s]
+ *   tin:   tin[s] = sum_{d=1..DB} Vb[s][d] X[s+d]       (skip when DB == 1: pass X to adsb_seg_correct_view)
+ *   correct (pass B):  out = xhat + Psi tin[s] + Xi din[s]; in == out allowed. */
+int adsb_seg_dseg_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
+                       const adsb_view* vin, double* const* dst, int ndst);
+int adsb_seg_din_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
+                      const adsb_view* vin, const double* dseg, double* din, double* const* xdst, int ndst);
+int adsb_seg_tin(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, long long lines, const double* X, double* tin);
+int adsb_seg_correct_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* in,
+                          const adsb_view* vin, double* out, const adsb_view* vout, const double* din,
+                          const double* tin_or_x);
 
 #ifdef __cplusplus
 }

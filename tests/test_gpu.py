@@ -310,6 +310,25 @@ def test_sharded_two_ranks_vs_oracle():
     assert "SHARDED_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_slab_two_ranks_vs_oracle():
+    """z-slabs with the distributed z substitution on 2 GPUs: symmetric memory, peer stores, signal barriers,
+    eager and through the captured CUDA graph (skipped on a 1-GPU box; the same code runs with virtual ranks
+    in test_slab_virtual_ranks_vs_oracle)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534",
+                        os.path.join(root, "tests", "slab_check.py")], capture_output=True, text=True, timeout=900)
+    assert "SLAB_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---------------------------------------------------------------------- thin slabs (8-GPU shards of small problems)
 @pytest.mark.parametrize("p,ne,planes", [(2, 30, 4), (2, 30, 8), (3, 21, 3), (2, 30, 16)])
 def test_thin_slab_views_match_whole_tensor(p, ne, planes):
@@ -368,3 +387,84 @@ def test_virtual_ranks_emulate_the_sharded_step(world, p, ne):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(world, p, ne) < (1e-12 if p == 2 else 2e-12)
+
+
+# ---------------------------------------------------------------------- segmented substitution
+def _segmented_sweep(ctx, axis, shape, bounds, data_dev, torch):
+    """pass A per segment, boundary states, pass B -- all segments on this GPU, in place on data_dev"""
+    from iga_ads_b200._lib import View
+
+    nx, ny, nz = shape
+    strides = [1, nx, nx * ny]
+    S = len(bounds) - 1
+    info = ctx.segment_info(axis, 0)
+    lines = nx * ny * nz // shape[axis]
+    f64 = dict(dtype=torch.float64, device=data_dev.device)
+    dseg = torch.zeros(S * info["KL"] * lines, **f64)
+    xst = torch.zeros(S * info["KD"] * lines, **f64)
+    din = torch.zeros(S * info["KL"] * lines, **f64)
+    tin = torch.zeros(S * info["KD"] * lines, **f64)
+    whole = View.make(list(shape), strides)
+    for s in range(S):
+        ext = list(shape)
+        ext[axis] = int(bounds[s + 1] - bounds[s])
+        ptr = data_dev.data_ptr() + 8 * int(bounds[s]) * strides[axis]
+        ctx.seg_sweep_view(axis, 0, s, ptr, View.make(ext, strides), ptr, View.make(ext, strides))
+    ctx.seg_dseg_view(axis, 0, 0, S, 0, data_dev.data_ptr(), whole, [dseg.data_ptr()])
+    ctx.seg_din_view(axis, 0, 0, S, 0, data_dev.data_ptr(), whole, dseg.data_ptr(), din.data_ptr(), [xst.data_ptr()])
+    back = xst
+    if info["DB"] > 1:
+        ctx.seg_tin(axis, 0, 0, S, lines, xst.data_ptr(), tin.data_ptr())
+        back = tin
+    ctx.seg_correct_view(axis, 0, 0, S, 0, data_dev.data_ptr(), whole, data_dev.data_ptr(), whole, din.data_ptr(),
+                         back.data_ptr())
+    ctx.synchronize()
+    return info
+
+
+@pytest.mark.parametrize("p,kind,h,fix,shape,S", [(2, 0, 0.0, 0, (66, 38, 70), 3), (3, 0, 0.0, 1, (53, 64, 40), 2),
+                                                  (5, 0, 0.0, 0, (69, 45, 75), 3), (3, 3, 1e-2 / 3, 0, (67, 43, 131), 4),
+                                                  (4, 0, 0.0, 0, (72, 36, 68), 4), (2, 0, 0.0, 0, (1026, 18, 20), 6)])
+def test_segmented_sweep_equals_dgbtrs(oracle, p, kind, h, fix, shape, S):
+    """every axis: pass A per segment + boundary kernels + pass B == dgbtrs over the whole line
+    (include/ads/lin/band_solve.hpp:21-31), for Gram, pivoting (p >= 4) and stiffness-augmented factors"""
+    import torch
+
+    from iga_ads_b200 import host
+
+    dev = torch.device("cuda", 0)
+    mats = [ads.matrix_1d(kind, p, s - p, h=h, fix=fix) for s in shape]
+    ctx = make_ctx(shape, mats, [p] * 3, [p] * 3)
+    rhs = np.random.default_rng(5).standard_normal(shape[::-1])  # [z][y][x]
+    for ax in range(3):
+        lu, piv = ads.band_factorize(mats[ax], p, p)
+        lines = np.moveaxis(rhs, 2 - ax, -1)
+        want = oracle.solve_factorized(lu, piv, p, p, np.ascontiguousarray(lines)).reshape(lines.shape)
+        want = np.moveaxis(want, -1, 2 - ax)
+        bounds = host.segment_bounds(piv, p, S)
+        ctx.set_segments(ax, 0, bounds)
+        data = torch.from_numpy(rhs.copy()).to(dev).reshape(-1)
+        info = _segmented_sweep(ctx, ax, shape, bounds, data, torch)
+        assert rel_l2(data.cpu().numpy(), want.ravel()) < 1e-13, (ax, info)
+
+
+@pytest.mark.parametrize("problem,world,p,ne,dt", [("heat_3d", 4, 2, 30, 1e-7), ("heat_3d", 8, 3, 45, 1e-7),
+                                                   ("heat_3d", 2, 2, 62, 1e-7), ("implicit_3d", 3, 3, 30, 1e-2),
+                                                   ("scalability_3d", 2, 2, 30, 1e-6), ("scalability_3d", 4, 5, 44, 1e-6),
+                                                   ("scalability_3d", 3, 4, 33, 1e-6), ("heat_3d", 1, 2, 20, 1e-7)])
+def test_slab_virtual_ranks_vs_oracle(oracle, problem, world, p, ne, dt):
+    """z-slabs with the distributed z substitution (iga_ads_b200/slab.py): `world` ranks in lockstep on this
+    GPU -- the kernels, peer-pointer stores and state arrays of a real run -- two steps against the oracle."""
+    from iga_ads_b200.slab import VirtualCluster
+
+    n = ne + p
+    u0 = synthetic_state((n, n, n))
+    cl = VirtualCluster(problem, p, ne, dt, world)
+    cl.set_state(u0)
+    sgn = np.random.default_rng(11).choice([-1.0, 1.0], size=u0.size)
+    for steps in (1, 2):
+        cl.step()
+        want, _ = oracle.run(problem, p, ne, dt, steps, u0=u0)
+        moved, _ = oracle.run(problem, p, ne, dt, steps, u0=np.nextafter(u0, u0 + sgn))
+        tol = steps * max(TOL_STEP, FLOOR_ULPS * rel_l2(moved, want))
+        assert rel_l2(cl.state(), want) < tol, (problem, world, steps, tol)
