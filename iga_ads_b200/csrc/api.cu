@@ -122,17 +122,22 @@ void free_factor(DevFactor& f) {
 }
 
 int upload_plan(const SweepPlan& P, SweepFactor& out, std::vector<void*>& allocs) {
-    double *cfF, *cfB, *cfC, *T, *Rm, *W, *V;
-    int* pv;
-    if (int rc = upload_vec(P.cfF, 0, &cfF, &allocs)) return rc;
-    if (int rc = upload_vec(P.cfB, 0, &cfB, &allocs)) return rc;
-    if (int rc = upload_vec(P.cfC, 0, &cfC, &allocs)) return rc;
+    // one blob: cfF | cfB | cfC | T | Rm | W | V, every piece padded to an even count (16 B granules)
+    const std::vector<double>* parts[7] = {&P.cfF, &P.cfB, &P.cfC, &P.T, &P.Rm, &P.W, &P.V};
+    std::vector<double> blob;
+    int off[7];
+    for (int i = 0; i < 7; ++i) {
+        off[i] = (int) blob.size();
+        blob.insert(blob.end(), parts[i]->begin(), parts[i]->end());
+        if (blob.size() & 1) blob.push_back(0.0);
+    }
+    double* d = nullptr;
+    int* pv = nullptr;
+    if (int rc = upload_vec(blob, 0, &d, &allocs)) return rc;
     if (int rc = upload_vec(P.pv, 0, &pv, &allocs)) return rc;
-    if (int rc = upload_vec(P.T, 0, &T, &allocs)) return rc;
-    if (int rc = upload_vec(P.Rm, 0, &Rm, &allocs)) return rc;
-    if (int rc = upload_vec(P.W, 0, &W, &allocs)) return rc;
-    if (int rc = upload_vec(P.V, 0, &V, &allocs)) return rc;
-    out = SweepFactor{cfF, cfB, cfC, pv, T, Rm, W, V, P.n, P.ST, P.SC, P.KL, P.KD, P.piv, P.DF, P.DB, P.seq};
+    out = SweepFactor{d + off[0], d + off[1], d + off[2], pv, d + off[3], d + off[4], d + off[5], d + off[6],
+                      P.n, P.ST, P.SC, P.KL, P.KD, P.piv, P.DF, P.DB, P.seq, (int) blob.size(),
+                      {off[1], off[2], off[3], off[4], off[5], off[6]}};
     return ADSB_OK;
 }
 
@@ -921,6 +926,11 @@ int seg_geom(const adsb_ctx* c, int axis, const double* in, const adsb_view& vi,
     G.row_base = row_base;
     G.s_lo = s_lo;
     G.s_hi = s_hi;
+    // contiguous lines (the z lines of an x-fastest tensor): number them flat, no idle lanes at row ends
+    if (G.s0_in == 1 && G.s0_out == 1 && G.s1_in == G.L0 && G.s1_out == G.L0 && (long long) G.L0 * G.L1 < (1ll << 30)) {
+        G.L0 *= G.L1;
+        G.L1 = 1;
+    }
     if (G.L1 > 65535) return fail(ADSB_EINVAL, "segments: outer extent beyond grid limits");
     (void) c;
     return ADSB_OK;

@@ -4,7 +4,35 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <utility>
+
 namespace adsb {
+
+// ADSB_PDL=0 switches programmatic dependent launch off (every kernel then starts after its predecessor ended)
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("ADSB_PDL");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+// Launch with the programmatic-stream-serialization attribute (see tma.cuh: pdl_wait / pdl_launch).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 constexpr int SWEEP_CH = 18;  // columns per chunk (one chunk per thread, held in registers)
 constexpr int SWEEP_RL = 2;   // lines per thread: they share every coefficient load and interleave for ILP
@@ -27,6 +55,11 @@ struct SweepFactor {
     const double* W;    // [SC][MAX_DEPTH-1][KL][KL]
     const double* V;    // [SC][MAX_DEPTH-1][KD][KD]
     int n, ST, SC, KL, KD, piv, DF, DB, seq;
+    // the seven tables above are pieces of ONE allocation (each padded to an even number of doubles), so a
+    // persistent CTA stages them with a single bulk copy: blob = cfF, blob_doubles in all, off[i] = start of
+    // cfB, cfC, T, Rm, W, V inside it
+    int blob_doubles;
+    int off[6];
 };
 
 // Lines of one sweep.  A line is addressed as base(l0, l1) + off(j):

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB)
         }
     }
     __syncthreads();
+    pdl_wait();  // everything above read constant tables only; the tensors belong to the previous kernel until here
 
     // TMA box of plane k: coordinates relative to the box `in` covers; everything outside is zero-filled
     const int c0 = x0 - PH - g.in_lo[0], c1 = y0 - P - g.in_lo[1], c2b = kb - g.in_lo[2];
@@ -407,7 +408,7 @@ int launch_cfg(const RhsOps& ops, const RhsGeom& g, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute((const void*) kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int) e;
     dim3 grid(tx, ty, nseg), block(C::NTH, 1, 1);
-    kern<<<grid, block, smem, st>>>(map, ops, g, zseg, zfirst);
+    if (cudaError_t e = launch_ex(kern, grid, block, smem, st, true, map, ops, g, zseg, zfirst); e != cudaSuccess) return (int) e;
     return (int) cudaGetLastError();
 }
 

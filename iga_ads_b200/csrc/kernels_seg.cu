@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace adsb {
 
@@ -34,6 +35,7 @@ __device__ __forceinline__ long long line_off(int l0, int l1, long long s0, long
 // One thread per (line, segment).
 template <int KL>
 __global__ void __launch_bounds__(256) seg_dseg_kernel(const SegDev T, const SegGeom G, DstList dst) {
+    pdl_wait();
     const int l0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int l1 = blockIdx.y;
     const int s = G.s_lo + blockIdx.z;
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) seg_dseg_kernel(const SegDev T, const Seg
 template <int KL, int KD>
 __global__ void __launch_bounds__(256)
     seg_din_kernel(const SegDev T, const SegGeom G, const double* __restrict__ dseg, double* __restrict__ din, DstList xdst) {
+    pdl_wait();
     const int l0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int l1 = blockIdx.y;
     const int s = G.s_lo + blockIdx.z;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(256)
 template <int KD>
 __global__ void __launch_bounds__(256)
     seg_tin_kernel(const SegDev T, int s_lo, long long L, const double* __restrict__ X, double* __restrict__ tin) {
+    pdl_wait();
     const long long line = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const int s = s_lo + blockIdx.y;
     if (line >= L) return;
@@ -118,6 +122,7 @@ template <int KL, int KD, int RC>
 __global__ void __launch_bounds__(128)
     seg_correct_strided(const SegDev T, const SegGeom G, const double* __restrict__ din, const double* __restrict__ tin,
                         int tin_is_x, int chunks_per_seg) {
+    pdl_wait();
     constexpr int KC = KD + KL;
     const int l0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int l1 = blockIdx.y;
@@ -147,11 +152,55 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Pass B when the lines of the view are contiguous in memory (l0 unit stride, l1 stride L0: the z sweep of an
+// x-fastest tensor): the lines are numbered flat, a thread owns TWO neighbouring lines (128-bit accesses) and
+// walks RC rows.  Blocks are ordered rows-fastest and from the LAST lines backwards: pass A finished with
+// those lines, so on a slab that is not much larger than the 126 MB L2 most of pass B's reads hit L2.
+template <int KL, int KD, int RC>
+__global__ void __launch_bounds__(128)
+    seg_correct_flat(const SegDev T, const SegGeom G, const double* __restrict__ din, const double* __restrict__ tin,
+                     int tin_is_x, int chunks_per_seg) {
+    pdl_wait();
+    constexpr int KC = KD + KL;
+    const long long L = (long long) G.L0 * G.L1;
+    const long long line = 2 * ((long long) (gridDim.y - 1 - blockIdx.y) * blockDim.x + threadIdx.x);
+    const int s = G.s_lo + blockIdx.x / chunks_per_seg, ck = blockIdx.x % chunks_per_seg;
+    const int a = T.bounds[s], b = T.bounds[s + 1];
+    const int j0 = a + ck * RC, j1 = min(b, j0 + RC);
+    if (line >= L || j0 >= j1) return;
+    double2 st[KC];  // tin | din of the two lines
+    const int ts = tin_is_x ? s + 1 : s;
+    const bool no_t = tin_is_x && s + 1 >= T.S;
+#pragma unroll
+    for (int k = 0; k < KD; ++k)
+        st[k] = no_t ? make_double2(0.0, 0.0) : __ldg(reinterpret_cast<const double2*>(tin + ((size_t) ts * KD + k) * L + line));
+#pragma unroll
+    for (int k = 0; k < KL; ++k) st[KD + k] = __ldg(reinterpret_cast<const double2*>(din + ((size_t) s * KL + k) * L + line));
+    const double* src = G.in + line + (long long) (j0 - G.row_base) * G.sj_in;
+    double* dst = G.out + line + (long long) (j0 - G.row_base) * G.sj_out;
+    const double* cf = T.cf + (size_t) j0 * KC;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+        double2 acc = __ldcs(reinterpret_cast<const double2*>(src));
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const double c = __ldg(cf + k);
+            acc.x = fma(c, st[k].x, acc.x);
+            acc.y = fma(c, st[k].y, acc.y);
+        }
+        __stcs(reinterpret_cast<double2*>(dst), acc);
+        src += G.sj_in;
+        dst += G.sj_out;
+        cf += KC;
+    }
+}
+
 // Pass B, sweep axis contiguous: a thread owns one row j of a segment and walks LB lines.
 template <int KL, int KD, int LB>
 __global__ void __launch_bounds__(128)
     seg_correct_contig(const SegDev T, const SegGeom G, const double* __restrict__ din, const double* __restrict__ tin,
                        int tin_is_x, int chunks_per_seg) {
+    pdl_wait();
     constexpr int KC = KD + KL;
     const int s = G.s_lo + blockIdx.x / chunks_per_seg, ck = blockIdx.x % chunks_per_seg;
     const int a = T.bounds[s], b = T.bounds[s + 1];
@@ -209,8 +258,7 @@ int launch_seg_dseg(const SegDev& T, const SegGeom& G, double* const* dst, int n
     return dispatch(T.KL, T.KD, [&](auto kl, auto) {
         constexpr int KL = decltype(kl)::value;
         dim3 block(128), grid((G.L0 + 127) / 128, G.L1, G.s_hi - G.s_lo);
-        seg_dseg_kernel<KL><<<grid, block, 0, st>>>(T, G, d);
-        return (int) cudaGetLastError();
+        return (int) launch_ex(seg_dseg_kernel<KL>, grid, block, 0, st, true, T, G, d);
     });
 }
 
@@ -221,8 +269,7 @@ int launch_seg_din(const SegDev& T, const SegGeom& G, const double* dseg, double
     return dispatch(T.KL, T.KD, [&](auto kl, auto kd) {
         constexpr int KL = decltype(kl)::value, KD = decltype(kd)::value;
         dim3 block(128), grid((G.L0 + 127) / 128, G.L1, G.s_hi - G.s_lo);
-        seg_din_kernel<KL, KD><<<grid, block, 0, st>>>(T, G, dseg, din, d);
-        return (int) cudaGetLastError();
+        return (int) launch_ex(seg_din_kernel<KL, KD>, grid, block, 0, st, true, T, G, dseg, din, d);
     });
 }
 
@@ -231,8 +278,7 @@ int launch_seg_tin(const SegDev& T, int s_lo, int s_hi, long long L, const doubl
     return dispatch(T.KL, T.KD, [&](auto, auto kd) {
         constexpr int KD = decltype(kd)::value;
         dim3 block(256), grid((unsigned) ((L + 255) / 256), s_hi - s_lo);
-        seg_tin_kernel<KD><<<grid, block, 0, st>>>(T, s_lo, L, X, tin);
-        return (int) cudaGetLastError();
+        return (int) launch_ex(seg_tin_kernel<KD>, grid, block, 0, st, true, T, s_lo, L, X, tin);
     });
 }
 
@@ -246,12 +292,22 @@ int launch_seg_correct(const SegDev& T, const SegGeom& G, const double* din, con
             const int cps = (max_rows + 127) / 128;
             const long long L = (long long) G.L0 * G.L1;
             dim3 block(128), grid(cps * (G.s_hi - G.s_lo), (unsigned) ((L + LB - 1) / LB));
-            seg_correct_contig<KL, KD, LB><<<grid, block, 0, st>>>(T, G, din, tin, tin_is_x, cps);
+            return (int) launch_ex(seg_correct_contig<KL, KD, LB>, grid, block, 0, st, true, T, G, din, tin, tin_is_x, cps);
         } else {
             constexpr int RC = 16;
             const int cps = (max_rows + RC - 1) / RC;
-            dim3 block(128), grid((G.L0 + 127) / 128, G.L1, cps * (G.s_hi - G.s_lo));
-            seg_correct_strided<KL, KD, RC><<<grid, block, 0, st>>>(T, G, din, tin, tin_is_x, cps);
+            const long long L = (long long) G.L0 * G.L1;
+            auto al16 = [](const void* p) { return ((uintptr_t) p & 15) == 0; };
+            const bool flat = G.s0_in == 1 && G.s0_out == 1 && (G.L1 == 1 || (G.s1_in == G.L0 && G.s1_out == G.L0)) &&
+                              L % 2 == 0 && G.sj_in % 2 == 0 && G.sj_out % 2 == 0 && al16(G.in) && al16(G.out) &&
+                              al16(din) && al16(tin) && (L + 255) / 256 <= 65535;
+            if (flat) {
+                dim3 block(128), grid(cps * (G.s_hi - G.s_lo), (unsigned) ((L + 255) / 256));
+                return (int) launch_ex(seg_correct_flat<KL, KD, RC>, grid, block, 0, st, true, T, G, din, tin, tin_is_x, cps);
+            } else {
+                dim3 block(128), grid((G.L0 + 127) / 128, G.L1, cps * (G.s_hi - G.s_lo));
+                return (int) launch_ex(seg_correct_strided<KL, KD, RC>, grid, block, 0, st, true, T, G, din, tin, tin_is_x, cps);
+            }
         }
         return (int) cudaGetLastError();
     });

@@ -50,33 +50,34 @@ template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
 __global__ void __launch_bounds__(288, 1)
     sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G) {
     constexpr int RL = SWEEP_RL, NLt = NL / RL;
-    constexpr int LF = sweep_pitch(KL), LB = sweep_pitch(KD + 1), LC = sweep_pitch(KD + KL);
-    constexpr int MD = SWEEP_MAX_DEPTH_DEV;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int SC = F0.SC;
     const int ncons = (int) blockDim.x - 32;
     const int tid = threadIdx.x;
     const int n = F0.n;
     const int tile_doubles = G.tile_doubles;
-    const int rows = SC * CH + KL + KD;  // rows of the coefficient tables (build_sweep_plan)
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* fst = tiles + (size_t) G.nbuf * tile_doubles;  // [SC][KL][NL]
     double* bst = fst + SC * KL * NL;                      // [SC][KD][NL]
-    double* s_cfF = bst + SC * KD * NL;
-    double* s_cfB = s_cfF + rows * LF;
-    double* s_cfC = s_cfB + rows * LB;
-    double* s_T = s_cfC + rows * LC;
-    double* s_Rm = s_T + SC * KL * KL;
-    double* s_W = s_Rm + SC * KD * KD;
-    double* s_V = s_W + SC * (MD - 1) * KL * KL;
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_V + SC * (MD - 1) * KD * KD);
+    double* s_tab = bst + SC * KD * NL;                    // the factor's tables, same layout as F0's blob
+    double* s_cfF = s_tab;
+    double* s_cfB = s_tab + F0.off[0];
+    double* s_cfC = s_tab + F0.off[1];
+    double* s_T = s_tab + F0.off[2];
+    double* s_Rm = s_tab + F0.off[3];
+    double* s_W = s_tab + F0.off[4];
+    double* s_V = s_tab + F0.off[5];
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_tab + F0.blob_doubles);
     uint64_t* done = full + MAX_NBUF;
+    uint64_t* tabbar = done + MAX_NBUF;
 
+    pdl_launch();  // every CTA of this grid is resident (one per SM): the next kernel's CTAs may queue up behind them
     if (tid == 0) {
         for (int b = 0; b < G.nbuf; ++b) {
             mbar_init(&full[b], 1);
             mbar_init(&done[b], 1);
         }
+        mbar_init(tabbar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
@@ -91,20 +92,17 @@ __global__ void __launch_bounds__(288, 1)
             const int pad0 = n * NL, pad = tile_doubles - pad0;
             for (int i = tid; i < G.nbuf * pad; i += ncons) tiles[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
         }
-        // the factor's tables: every tile of this persistent CTA uses them
-        for (int i = tid; i < rows * LF; i += ncons) s_cfF[i] = F0.cfF[i];
-        for (int i = tid; i < rows * LB; i += ncons) s_cfB[i] = F0.cfB[i];
-        for (int i = tid; i < rows * LC; i += ncons) s_cfC[i] = F0.cfC[i];
-        for (int i = tid; i < SC * KL * KL; i += ncons) s_T[i] = F0.T[i];
-        for (int i = tid; i < SC * KD * KD; i += ncons) s_Rm[i] = F0.Rm[i];
-        for (int i = tid; i < SC * (MD - 1) * KL * KL; i += ncons) s_W[i] = F0.W[i];
-        for (int i = tid; i < SC * (MD - 1) * KD * KD; i += ncons) s_V[i] = F0.V[i];
         sweep_sync(ncons);
+        mbar_wait(tabbar, 0);  // the factor's tables (one bulk copy issued by the producer) have landed
     }
 
     if (tid >= ncons) {
         // ------------------------------------------------------------------ producer warp
         if (tid != ncons) return;
+        // the factor's tables first: every tile of this persistent CTA uses them (one bulk copy, UBLKCP)
+        mbar_expect_tx(tabbar, (uint32_t) (F0.blob_doubles * 8));
+        bulk_g2s(s_tab, F0.cfF, (uint32_t) (F0.blob_doubles * 8), tabbar);
+        pdl_wait();  // the tensor itself: only once the previous kernel of the stream has finished with it
         auto issue_load = [&](int i) {
             const int t = blockIdx.x + i * gridDim.x;
             const int bx = t % G.nb0, m = t / G.nb0;
@@ -418,11 +416,9 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
         T.maps = it->second;
     }
     T.tile_doubles = (T.tile_doubles + 15) & ~15;  // 128 B granules
-    const int LF = sweep_pitch(F.KL), LB = sweep_pitch(F.KD + 1), LC = sweep_pitch(F.KD + F.KL);
-    const int rows = F.SC * SWEEP_CH + F.KL + F.KD;
-    const size_t fixed_doubles = (size_t) F.SC * (F.KL + F.KD) * NL + (size_t) rows * (LF + LB + LC) +
-                                 (size_t) F.SC * (F.KL * F.KL + F.KD * F.KD) * SWEEP_MAX_DEPTH_DEV;
-    const size_t fixed_bytes = fixed_doubles * 8 + 2 * MAX_NBUF * 8 + 64;
+    const size_t fixed_doubles = (size_t) F.SC * (F.KL + F.KD) * NL + (size_t) F.blob_doubles;
+    const size_t fixed_bytes = fixed_doubles * 8 + (2 * MAX_NBUF + 1) * 8 + 64;
+    if ((uintptr_t) F.cfF % 16 != 0 || F.blob_doubles % 2 != 0) return -1;
     const size_t budget = 226 * 1024;
     if (fixed_bytes + 2 * (size_t) T.tile_doubles * 8 > budget) return -1;
     int nbuf = (int) ((budget - fixed_bytes) / ((size_t) T.tile_doubles * 8));
@@ -445,8 +441,7 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
     dim3 block(ncons + 32, 1, 1);
     const int cap = (G.max_ctas > 0 && G.max_ctas < sms) ? G.max_ctas : sms;
     dim3 grid(T.ntiles < cap ? T.ntiles : cap, 1, 1);
-    k<<<grid, block, smem, st>>>(F, T);
-    return (int) cudaGetLastError();
+    return (int) launch_ex(k, grid, block, smem, st, true, F, T);
 }
 
 }  // namespace adsb

@@ -40,6 +40,14 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with launch_ex(..., pdl = true) may start
+// while its predecessor in the stream is still draining -- its prologue (barrier init, staging of constant
+// tables) overlaps the predecessor's tail -- and must call pdl_wait() before it touches any memory the
+// predecessor reads or writes.  pdl_launch() in the predecessor lets the dependent grid be scheduled from
+// that point on (otherwise: when the predecessor's blocks exit).  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace adsb
 
 #endif

@@ -114,7 +114,8 @@ class SlabSim:
         nx, ny, nz = self.n
         self.pitch = nx + (nx & 1)           # x rows padded to 16 B (TMA), as the managed tensors are
         self.plane = ny * self.pitch         # doubles per z plane
-        self.lines = nx * ny                 # z lines; state arrays are [S][K][lines], line = x + nx*y
+        self.lines = self.pitch * ny         # z lines incl. the pad column (contiguous: the boundary kernels and
+        #                                      pass B number them flat); state arrays are [S][K][lines]
         # ---- factors: let the model factorise exactly as on one GPU, but capture instead of uploading
         self.factors = {}
 
@@ -190,6 +191,10 @@ class SlabSim:
     # ---- geometry helpers
     def _view(self, planes):
         return View.make([self.n[0], self.n[1], planes], [1, self.pitch, self.plane])
+
+    def _view_lines(self, planes):
+        """the same memory with the pad column counted in: every z plane is one contiguous run of lines"""
+        return View.make([self.pitch, self.n[1], planes], [1, self.pitch, self.plane])
 
     def halo(self, k):
         return self.sym["h1" if k else "h0"]
@@ -269,7 +274,7 @@ class SlabSim:
         DF = self.seg[slot]["DF"]
         dst = [self.peers.ptr(q, "dseg") for q in range(self.rank + 1, min(self.world, self.rank + DF + 1))]
         if dst:
-            self.ctx.seg_dseg_view(2, slot, self.rank, self.rank + 1, self.z0, wk, v, dst)
+            self.ctx.seg_dseg_view(2, slot, self.rank, self.rank + 1, self.z0, wk, self._view_lines(self.cz), dst)
             self.exchange_bytes += 8 * self.seg[slot]["KL"] * self.lines * len(dst)
             self.launches += 1
         self.launches += 4
@@ -282,7 +287,7 @@ class SlabSim:
         slot = int(sub.slots[2])
         DB = self.seg[slot]["DB"]
         dst = [self.sym["x"].data_ptr()] + [self.peers.ptr(q, "x") for q in range(max(0, self.rank - DB), self.rank)]
-        self.ctx.seg_din_view(2, slot, self.rank, self.rank + 1, self.z0, self.work.data_ptr(), self._view(self.cz),
+        self.ctx.seg_din_view(2, slot, self.rank, self.rank + 1, self.z0, self.work.data_ptr(), self._view_lines(self.cz),
                               self.sym["dseg"].data_ptr(), self.din.data_ptr(), dst)
         self.exchange_bytes += 8 * self.seg[slot]["KD"] * self.lines * (len(dst) - 1)
         self.launches += 1
@@ -292,7 +297,7 @@ class SlabSim:
         """pass B into the interior of the other state buffer; swap; publish the new boundary planes"""
         nxt = 1 - self.cur
         out_ptr = self.interior(nxt).data_ptr()
-        v = self._view(self.cz)
+        v = self._view_lines(self.cz)
         if self.world == 1:
             self.interior(nxt).copy_(self.work, non_blocking=True)
         else:
