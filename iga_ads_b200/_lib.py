@@ -62,6 +62,15 @@ class View(ctypes.Structure):
         return cls((c_int * 3)(*n), (c_ll * 3)(*s))
 
 
+class DistArgs(ctypes.Structure):
+    """adsb_dist_args (include/adsb200.h): one rank's arguments of the fused distributed sweep"""
+    _fields_ = [("rank", c_int), ("nranks", c_int), ("nl", c_int), ("lag", c_int), ("sync_words", vp),
+                ("dseg_local", vp), ("x_local", vp), ("dseg_next", vp), ("x_prev", vp),
+                ("flags_local", vp), ("flags_next", vp), ("flags_prev", vp), ("error_flag", vp)]
+
+
+DIST_FLAGS = 512
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "adsb_abi_version": (c_int, []),
@@ -107,6 +116,8 @@ _SIGNATURES = {
     "adsb_set_axis_segments": (c_int, [vp, c_int, c_int, c_int, ip, c_int, c_int]),
     "adsb_segment_info": (c_int, [vp, c_int, c_int, ip]),
     "adsb_seg_sweep_view": (c_int, [vp, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp, ctypes.POINTER(View)]),
+    "adsb_dist_sweep_view": (c_int, [vp, c_int, c_int, vp, ctypes.POINTER(View), ctypes.POINTER(DistArgs)]),
+    "adsb_dist_sweep_check": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(View), c_int, c_int]),
     "adsb_seg_dseg_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View),
                                    ctypes.POINTER(vp), c_int]),
     "adsb_seg_din_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp, vp,

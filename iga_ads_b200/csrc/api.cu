@@ -956,7 +956,8 @@ int adsb_set_axis_segments(adsb_ctx* c, int axis, int slot, int nseg, const int*
     if (int rc = select_device(c)) return rc;
     DevFactor& D = c->ax[axis].fac[slot];
     SegPlan P;
-    if (int rc = build_segment_plan(D.n, D.kl, D.ku, D.ldab, D.ab.data(), D.ipiv.data(), nseg, bounds, 1e-20, P)) return rc;
+    // chain cut-off 1e-17: dropped products change the result by less than a tenth of the unit round-off
+    if (int rc = build_segment_plan(D.n, D.kl, D.ku, D.ldab, D.ab.data(), D.ipiv.data(), nseg, bounds, 1e-17, P)) return rc;
     CU(cudaStreamSynchronize(c->stream));
     free_segments(D.seg);
     SegSet& g = D.seg;
@@ -1005,6 +1006,72 @@ int adsb_seg_sweep_view(adsb_ctx* c, int axis, int slot, int seg, const double* 
         return fail(ADSB_EINVAL, "seg_sweep_view: segment is not local to this context");
     if (int rc = select_device(c)) return rc;
     return sweep_impl(c, axis, slot, in, *vin, nullptr, out, *vout, nullptr, false, &g->local[seg - g->local_lo]);
+}
+
+int adsb_dist_sweep_check(adsb_ctx* c, int axis, int slot, int rank, const adsb_view* v, int nl, int lag) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!v || rank < g->local_lo || rank >= g->local_lo + g->local_cnt) return fail(ADSB_EINVAL, "dist_sweep_check: bad argument");
+    const SweepFactor& F = g->local[rank - g->local_lo];
+    if (v->n[axis] != F.n || v->s[axis] == 1) return 0;
+    const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+    const int l0 = (v->s[a] <= v->s[b]) ? a : b, l1 = (l0 == a) ? b : a;
+    SweepGeom G{};
+    G.sj_in = G.sj_out = v->s[axis];
+    G.L0 = v->n[l0];
+    G.L1 = v->n[l1];
+    G.s0_in = G.s0_out = v->s[l0];
+    G.s1_in = G.s1_out = v->s[l1];
+    if (G.s0_in != 1 || (G.sj_in & 1) || (G.s1_in & 1)) return 0;
+    SweepDistArgs D{};
+    D.lag = lag > 0 ? lag : 4;
+    return launch_sweep_dist(F, g->dev, G, D, nl, nullptr, true) == 0 ? 1 : 0;
+}
+
+int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const adsb_view* v, const adsb_dist_args* d) {
+    SegSet* g;
+    if (int rc = seg_of(c, axis, slot, &g)) return rc;
+    if (!data || !v || !d) return fail(ADSB_EINVAL, "dist_sweep_view: null argument");
+    static_assert(ADSB_DIST_FLAGS == 2 * ADSB_DIST_MAX_CTAS, "flag array size out of sync");
+    if (d->rank < g->local_lo || d->rank >= g->local_lo + g->local_cnt || d->nranks != g->dev.S)
+        return fail(ADSB_EINVAL, "dist_sweep_view: rank is not a local segment of this context");
+    if (!d->dseg_local || !d->x_local || !d->flags_local || !d->sync_words || (d->rank > 0 && (!d->x_prev || !d->flags_prev)) ||
+        (d->rank + 1 < d->nranks && (!d->dseg_next || !d->flags_next)))
+        return fail(ADSB_EINVAL, "dist_sweep_view: missing state / flag arrays");
+    if (int rc = select_device(c)) return rc;
+    const SweepFactor& F = g->local[d->rank - g->local_lo];
+    if (v->n[axis] != F.n) return fail(ADSB_EINVAL, "dist_sweep_view: the view does not span the slab");
+    if (v->s[axis] == 1) return fail(ADSB_EINVAL, "dist_sweep_view: the sharded axis must not be the contiguous one");
+    const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+    const int l0 = (v->s[a] <= v->s[b]) ? a : b, l1 = (l0 == a) ? b : a;
+    SweepGeom G{};
+    G.in = data;
+    G.out = data;
+    G.sj_in = G.sj_out = v->s[axis];
+    G.L0 = v->n[l0];
+    G.L1 = v->n[l1];
+    G.s0_in = G.s0_out = v->s[l0];
+    G.s1_in = G.s1_out = v->s[l1];
+    G.max_ctas = c->sm_limit;
+    SweepDistArgs D{};
+    D.rank = d->rank;
+    D.row_base = g->bounds[d->rank];
+    D.lag = d->lag > 0 ? d->lag : 4;
+    D.sync_words = d->sync_words;
+    D.dseg_local = d->dseg_local;
+    D.x_local = d->x_local;
+    D.dseg_next = d->rank + 1 < d->nranks ? d->dseg_next : nullptr;
+    D.x_prev = d->rank > 0 ? d->x_prev : nullptr;
+    D.flags_local = d->flags_local;
+    D.flags_next = d->rank + 1 < d->nranks ? d->flags_next : nullptr;
+    D.flags_prev = d->rank > 0 ? d->flags_prev : nullptr;
+    D.error_flag = d->error_flag;
+    StageTimer t(c, 1 + axis);
+    const int rc = launch_sweep_dist(F, g->dev, G, D, d->nl, c->stream);
+    if (rc == -1) return fail(ADSB_ESTATE, "dist_sweep_view: this factor / view is not eligible for the fused kernel");
+    if (rc != 0) return cuda_fail((cudaError_t) rc, "distributed sweep kernel launch");
+    c->launches++;
+    return ADSB_OK;
 }
 
 int adsb_seg_dseg_view(adsb_ctx* c, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,

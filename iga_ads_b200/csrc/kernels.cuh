@@ -105,6 +105,9 @@ struct SweepTileGeom {
 int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
                       const long long* off_out_h, cudaStream_t st);
 
+int sweep_strided_maps(const SweepGeom& G, int n, int NL, const long long* off_in_h, const long long* off_out_h,
+                       cudaStream_t st, SweepTileGeom& T);
+
 // returns cudaError_t as int
 int launch_sweep(const SweepFactor& F, const SweepGeom& G, bool contig, int NLt, cudaStream_t st);
 int sweep_smem_bytes(const SweepFactor& F, bool contig, int NLt, int pitch);
@@ -200,6 +203,26 @@ int launch_seg_tin(const SegDev& T, int s_lo, int s_hi, long long L, const doubl
 // max_rows: longest segment among [s_lo, s_hi); tin_is_x: chain depth 1, `tin` is the X array itself
 int launch_seg_correct(const SegDev& T, const SegGeom& G, const double* din, const double* tin, int tin_is_x,
                        int max_rows, cudaStream_t st);
+
+// Fused distributed sweep (kernels_sweep_dist.cu): one rank's arguments.  State arrays are [S][K][lines];
+// flag arrays hold 2 * ADSB_DIST_MAX_CTAS counters (forward values from the previous rank, backward values from
+// the next one), one per CTA.
+constexpr int ADSB_DIST_MAX_CTAS = 256;
+struct SweepDistArgs {
+    int rank, row_base, lag;
+    unsigned long long* sync_words;  // [0] launch epoch (>= 1), [1] CTAs finished in the running launch
+    double* dseg_local;
+    double* x_local;
+    double* dseg_next;  // state array of rank + 1 (peer pointer), nullptr on the last rank
+    double* x_prev;     // state array of rank - 1, nullptr on the first rank
+    unsigned long long* flags_local;
+    unsigned long long* flags_next;
+    unsigned long long* flags_prev;
+    int* error_flag;
+};
+// dry_run: only report eligibility (0 / -1), launch nothing
+int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
+                      cudaStream_t st, bool dry_run = false);
 
 // vnx > 0: `values` are the first elements of a tensor with x rows of vnx doubles, vpitch apart (else dense)
 int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,

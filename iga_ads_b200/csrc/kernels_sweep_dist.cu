@@ -1,0 +1,437 @@
+// kernels_sweep_dist.cu -- K2 for a slab-sharded axis: the banded substitution along lines that are cut across
+// GPUs, in ONE pass over the slab, fused with its boundary exchange over NVLink.
+//
+// Every rank runs this kernel on its own slab (one segment of every line; tables: build_segment_plan).  The
+// algebra is the segmented substitution of kernels_seg.cu -- pass A (the slab's own columns of the factor),
+// the KL forward / KD backward boundary values per line, pass B (x = xhat + Xi din + Psi tin) -- i.e. the
+// recurrence of lin::solve_with_factorized -> dgbtrs_ (include/ads/lin/band_solve.hpp:21-31) with the same
+// factor and pivots.  What is new is the schedule: the three stages run software-pipelined inside one
+// persistent kernel, tile by tile, and talk to the neighbouring GPUs through peer pointers:
+//
+//   iteration i of a CTA (tile sequence identical on all ranks, CTA b pairs with CTA b of the neighbours):
+//     A (tile i)       TMA load, local substitution in shared memory, TMA store of xhat in place;
+//                      Dseg = E * xhat[last KL rows] stored into the NEXT rank's state array, then a
+//                      release flag on that rank ("tile i of CTA b: forward values are there")
+//     B1 (tile i-K)    wait for the PREVIOUS rank's flag, din <- its Dseg; X = xhat[first KD rows] + XiF din
+//                      stored into the previous rank's state array + flag
+//     B2 (tile i-2K)   wait for the NEXT rank's flag, tin <- its X; the tile comes back by TMA (an L2 hit: it
+//                      was stored 2K tiles ago), x += Psi tin + Xi din in shared memory, TMA store in place
+//
+// so the NVLink round trips (a few microseconds) hide behind K tiles of work, the slab is read from HBM once
+// and written once (16 B/DOF: the intermediate xhat lives in L2 -- 2K tiles per CTA, tens of MB in all), and no
+// host-side barrier separates the stages.  Two producer warps feed the two tile rings; the consumer warps run
+// A, B1, B2 back to back.  Flags carry the launch epoch, so they never need resetting; the epoch is a device
+// counter advanced by the last CTA to finish (a replayed CUDA graph cannot carry it as a kernel argument).
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "sweep_core.cuh"
+
+namespace adsb {
+
+namespace {
+
+constexpr int DIST_NBUF = 2;  // slots per tile ring
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_volatile(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= want; gives up after ~2 s (sets *err, the results are then garbage but nothing hangs)
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long want, int* err) {
+    long long t0 = clock64();
+    unsigned ns = 20;
+    while (ld_acquire_sys(flag) < want) {
+        __nanosleep(ns);
+        if (ns < 400) ns *= 2;
+        if (clock64() - t0 > 4000000000ll) {
+            if (err) atomicExch(err, 1);
+            break;
+        }
+    }
+}
+
+template <int KL, int KD, bool PIV, int CH, int NL>
+__global__ void __launch_bounds__(352, 1)
+    sweep_dist_kernel(const SweepFactor F0, const SegDev T, const SweepTileGeom G, const SweepDistArgs D) {
+    constexpr int RL = SWEEP_RL, NLt = NL / RL, KC = KD + KL;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int SC = F0.SC, n = F0.n;
+    const int ncons = (int) blockDim.x - 64;
+    const int tid = threadIdx.x;
+    const int tile_doubles = G.tile_doubles;
+    const int K = D.lag;
+    const int r = D.rank, S = T.S;
+    double* ringA = reinterpret_cast<double*>(smem_raw);
+    double* ringD = ringA + (size_t) DIST_NBUF * tile_doubles;
+    double* fst = ringD + (size_t) DIST_NBUF * tile_doubles;  // [SC][KL][NL]
+    double* bst = fst + SC * KL * NL;                         // [SC][KD][NL]
+    double* s_tab = bst + SC * KD * NL;                       // factor tables (blob layout)
+    double* s_cf = s_tab + F0.blob_doubles;                   // [n][KC]   Psi | Xi of the slab's rows
+    double* s_E = s_cf + ((n * KC + 1) & ~1);                 // [KL][KL]
+    double* s_XiF = s_E + ((KL * KL + 1) & ~1);               // [KD][KL]
+    double* s_xf = s_XiF + ((KD * KL + 1) & ~1);              // [K+1][KD][NL]   xhat first rows of tiles between A and B1
+    double* s_din = s_xf + (K + 1) * KD * NL;                 // [2K+1][KL][NL]  din of tiles between B1 and B2
+    double* s_tin = s_din + (2 * K + 1) * KL * NL;            // [KD][NL]
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(s_tin + KD * NL);
+    uint64_t* doneA = fullA + DIST_NBUF;
+    uint64_t* fullD = doneA + DIST_NBUF;
+    uint64_t* doneD = fullD + DIST_NBUF;
+    uint64_t* tabbar = doneD + DIST_NBUF;
+    volatile int* stored = reinterpret_cast<volatile int*>(tabbar + 1);  // tiles whose pass-A store is complete
+
+    pdl_launch();
+    if (tid == 0) {
+        for (int b = 0; b < DIST_NBUF; ++b) {
+            mbar_init(&fullA[b], 1);
+            mbar_init(&doneA[b], 1);
+            mbar_init(&fullD[b], 1);
+            mbar_init(&doneD[b], 1);
+        }
+        mbar_init(tabbar, 1);
+        *stored = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int my_count = (G.ntiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(G.maps);
+    auto tile_of = [&](int i, int& bx, int& m) {
+        const int t = blockIdx.x + i * gridDim.x;
+        bx = t % G.nb0;
+        m = t / G.nb0;
+    };
+
+    if (tid >= ncons) {
+        if (tid == ncons) {
+            // ---------------------------------------------------------------- producer of ring A (pass A)
+            mbar_expect_tx(tabbar, (uint32_t) (F0.blob_doubles * 8));
+            bulk_g2s(s_tab, F0.cfF, (uint32_t) (F0.blob_doubles * 8), tabbar);
+            pdl_wait();
+            auto load = [&](int i) {
+                int bx, m;
+                tile_of(i, bx, m);
+                const int b = i % DIST_NBUF;
+                double* dst = ringA + (size_t) b * tile_doubles;
+                mbar_expect_tx(&fullA[b], (uint32_t) G.load_bytes);
+                for (int k = 0; k < G.nbox_in; ++k) tma_load_3d(dst + G.row0_in[k] * NL, maps + k, bx * NL, 0, m, &fullA[b]);
+            };
+            auto store = [&](int i) {
+                int bx, m;
+                tile_of(i, bx, m);
+                const double* src = ringA + (size_t) (i % DIST_NBUF) * tile_doubles;
+                for (int k = 0; k < G.nbox_out; ++k)
+                    tma_store_3d(maps + G.nbox_in + k, bx * NL, 0, m, src + G.row0_out[k] * NL);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            };
+            for (int i = 0; i < DIST_NBUF - 1 && i < my_count; ++i) load(i);
+            for (int j = 0; j < my_count; ++j) {
+                if (j + DIST_NBUF - 1 < my_count) {
+                    if (j >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    load(j + DIST_NBUF - 1);
+                }
+                mbar_wait(&doneA[j % DIST_NBUF], (uint32_t) ((j / DIST_NBUF) & 1));
+                store(j);
+                // all but the two most recent stores have reached memory: tiles 0 .. j-2 may be read back
+                // (pass B trails by 2K >= 2 tiles, so this never holds the ring up)
+                asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+                if (j >= 1) *stored = j - 1;
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence_block();
+            *stored = my_count;
+        } else if (tid == ncons + 32) {
+            // ---------------------------------------------------------------- producer of ring D (pass B)
+            pdl_wait();
+            auto load = [&](int i) {
+                while (*stored < i + 1) __nanosleep(40);  // pass A's store of this tile is complete
+                int bx, m;
+                tile_of(i, bx, m);
+                const int b = i % DIST_NBUF;
+                double* dst = ringD + (size_t) b * tile_doubles;
+                mbar_expect_tx(&fullD[b], (uint32_t) G.load_bytes);
+                // pass A stored through the `out` maps: read the tile back through the same ones
+                for (int k = 0; k < G.nbox_out; ++k)
+                    tma_load_3d(dst + G.row0_out[k] * NL, maps + G.nbox_in + k, bx * NL, 0, m, &fullD[b]);
+            };
+            auto store = [&](int i) {
+                int bx, m;
+                tile_of(i, bx, m);
+                const double* src = ringD + (size_t) (i % DIST_NBUF) * tile_doubles;
+                for (int k = 0; k < G.nbox_out; ++k)
+                    tma_store_3d(maps + G.nbox_in + k, bx * NL, 0, m, src + G.row0_out[k] * NL);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            };
+            for (int i = 0; i < DIST_NBUF - 1 && i < my_count; ++i) load(i);
+            for (int j = 0; j < my_count; ++j) {
+                if (j + DIST_NBUF - 1 < my_count) {
+                    if (j >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    load(j + DIST_NBUF - 1);
+                }
+                mbar_wait(&doneD[j % DIST_NBUF], (uint32_t) ((j / DIST_NBUF) & 1));
+                store(j);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    // set-up: pad rows of both rings (rows past the slab read as zero), segment tables of this slab
+    {
+        const int pad0 = n * NL, pad = tile_doubles - pad0;
+        for (int i = tid; i < 2 * DIST_NBUF * pad; i += ncons) ringA[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
+        const int a = D.row_base;
+        for (int i = tid; i < n * KC; i += ncons) s_cf[i] = T.cf[(size_t) a * KC + i];
+        for (int i = tid; i < KL * KL; i += ncons) s_E[i] = T.E[(size_t) r * KL * KL + i];
+        for (int i = tid; i < KD * KL; i += ncons) s_XiF[i] = T.XiF[(size_t) r * KD * KL + i];
+        sweep_sync(ncons);
+        mbar_wait(tabbar, 0);
+    }
+    SweepFactor F = F0;
+    F.cfF = s_tab;
+    F.cfB = s_tab + F0.off[0];
+    F.cfC = s_tab + F0.off[1];
+    F.T = s_tab + F0.off[2];
+    F.Rm = s_tab + F0.off[3];
+    F.W = s_tab + F0.off[4];
+    F.V = s_tab + F0.off[5];
+    const int tx = tid % NLt;
+    const int craw = tid / NLt;
+    const int c = min(craw, SC - 1);  // padding threads shadow the last chunk in pass A (identical values)
+    const int j0 = c * CH;
+    const long long L = (long long) G.L0 * G.L1;
+    // launch epoch: every CTA reads it before the last one to finish can advance it
+    const unsigned long long base = *reinterpret_cast<volatile unsigned long long*>(D.sync_words) << 32;
+    unsigned long long* flagA_in = D.flags_local + blockIdx.x;                         // written by rank r-1
+    unsigned long long* flagB_in = D.flags_local + ADSB_DIST_MAX_CTAS + blockIdx.x;    // written by rank r+1
+    unsigned long long* flagA_out = D.flags_next ? D.flags_next + blockIdx.x : nullptr;
+    unsigned long long* flagB_out = D.flags_prev ? D.flags_prev + ADSB_DIST_MAX_CTAS + blockIdx.x : nullptr;
+
+    for (int it = 0; it < my_count + 2 * K; ++it) {
+        // ================================================================== A: tile it
+        if (it < my_count) {
+            const int b = it % DIST_NBUF;
+            double* tile = ringA + (size_t) b * tile_doubles;
+            mbar_wait(&fullA[b], (uint32_t) ((it / DIST_NBUF) & 1));
+            double v[RL][CH + KL];
+            {
+                const double* mine = tile + (size_t) j0 * NL + 2 * tx;
+#pragma unroll
+                for (int q = 0; q < CH + KL; ++q) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(mine + q * NL);
+                    v[0][q] = t2.x;
+                    v[1][q] = t2.y;
+                }
+            }
+            sweep_core<KL, KD, PIV, CH, RL, true>(F, v, fst, bst, c, tx, NLt, SC, ncons);
+            {
+                double* mine = tile + (size_t) j0 * NL + 2 * tx;
+#pragma unroll
+                for (int q = 0; q < CH; ++q)
+                    if (j0 + q < n) *reinterpret_cast<double2*>(mine + q * NL) = make_double2(v[0][q], v[1][q]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            sweep_sync(ncons);
+            // the tile is final for pass A: keep its first KD rows for B1, send Dseg to the next rank
+            int bx, m;
+            tile_of(it, bx, m);
+            const long long line0 = (long long) bx * NL + (long long) m * G.L0;
+            const int lanes = min(NL, G.L0 - bx * NL);
+            double* xf = s_xf + (size_t) (it % (K + 1)) * KD * NL;
+            for (int i = tid; i < KD * NL; i += ncons) xf[i] = tile[i];  // rows 0 .. KD-1 are the first KD*NL doubles
+            if (D.dseg_next) {
+                for (int i = tid; i < KL * NL; i += ncons) {
+                    const int kk = i / NL, ln = i % NL;
+                    if (ln < lanes) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int mm = 0; mm < KL; ++mm) acc = fma(s_E[kk * KL + mm], tile[(size_t) (n - KL + mm) * NL + ln], acc);
+                        D.dseg_next[((size_t) r * KL + kk) * L + line0 + ln] = acc;
+                    }
+                }
+                __threadfence_system();
+            }
+            sweep_sync(ncons);
+            if (tid == 0) {
+                mbar_arrive(&doneA[b]);
+                if (flagA_out) st_release_sys(flagA_out, base + (unsigned long long) it + 1);
+            }
+        }
+        // ================================================================== B1: tile it - K
+        const int j1 = it - K;
+        if (j1 >= 0 && j1 < my_count) {
+            int bx, m;
+            tile_of(j1, bx, m);
+            const long long line0 = (long long) bx * NL + (long long) m * G.L0;
+            const int lanes = min(NL, G.L0 - bx * NL);
+            double* dn = s_din + (size_t) (j1 % (2 * K + 1)) * KL * NL;
+            if (r > 0) {
+                if (tid == 0) wait_flag(flagA_in, base + (unsigned long long) j1 + 1, D.error_flag);
+                sweep_sync(ncons);
+            }
+            for (int i = tid; i < KL * NL; i += ncons) {
+                const int kk = i / NL, ln = i % NL;
+                dn[i] = (r > 0 && ln < lanes) ? ld_volatile(D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + line0 + ln) : 0.0;
+            }
+            sweep_sync(ncons);
+            if (D.x_prev) {
+                const double* xf = s_xf + (size_t) (j1 % (K + 1)) * KD * NL;
+                for (int i = tid; i < KD * NL; i += ncons) {
+                    const int ii = i / NL, ln = i % NL;
+                    if (ln < lanes) {
+                        double acc = xf[i];
+#pragma unroll
+                        for (int q = 0; q < KL; ++q) acc = fma(s_XiF[ii * KL + q], dn[q * NL + ln], acc);
+                        D.x_prev[((size_t) r * KD + ii) * L + line0 + ln] = acc;
+                    }
+                }
+                __threadfence_system();
+                sweep_sync(ncons);
+                if (tid == 0) st_release_sys(flagB_out, base + (unsigned long long) j1 + 1);
+            }
+        }
+        // ================================================================== B2: tile it - 2K
+        const int j2 = it - 2 * K;
+        if (j2 >= 0 && j2 < my_count) {
+            int bx, m;
+            tile_of(j2, bx, m);
+            const long long line0 = (long long) bx * NL + (long long) m * G.L0;
+            const int lanes = min(NL, G.L0 - bx * NL);
+            const int b = j2 % DIST_NBUF;
+            double* tile = ringD + (size_t) b * tile_doubles;
+            const double* dn = s_din + (size_t) (j2 % (2 * K + 1)) * KL * NL;
+            if (r + 1 < S) {
+                if (tid == 0) wait_flag(flagB_in, base + (unsigned long long) j2 + 1, D.error_flag);
+                sweep_sync(ncons);
+            }
+            for (int i = tid; i < KD * NL; i += ncons) {
+                const int ii = i / NL, ln = i % NL;
+                s_tin[i] = (r + 1 < S && ln < lanes) ? ld_volatile(D.x_local + ((size_t) (r + 1) * KD + ii) * L + line0 + ln) : 0.0;
+            }
+            mbar_wait(&fullD[b], (uint32_t) ((j2 / DIST_NBUF) & 1));
+            sweep_sync(ncons);
+            if (craw < SC) {
+                double2 st[KC];
+#pragma unroll
+                for (int k = 0; k < KD; ++k) st[k] = *reinterpret_cast<const double2*>(s_tin + k * NL + 2 * tx);
+#pragma unroll
+                for (int k = 0; k < KL; ++k) st[KD + k] = *reinterpret_cast<const double2*>(dn + k * NL + 2 * tx);
+                double* mine = tile + (size_t) j0 * NL + 2 * tx;
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    if (j0 + q < n) {
+                        double2 acc = *reinterpret_cast<const double2*>(mine + q * NL);
+                        const double* cf = s_cf + (size_t) (j0 + q) * KC;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            acc.x = fma(cf[k], st[k].x, acc.x);
+                            acc.y = fma(cf[k], st[k].y, acc.y);
+                        }
+                        *reinterpret_cast<double2*>(mine + q * NL) = acc;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            sweep_sync(ncons);
+            if (tid == 0) mbar_arrive(&doneD[b]);
+        }
+    }
+    if (tid == 0) {
+        unsigned int* done_ctas = reinterpret_cast<unsigned int*>(D.sync_words + 1);
+        __threadfence();
+        if (atomicAdd(done_ctas, 1u) == gridDim.x - 1) {
+            *done_ctas = 0;
+            *reinterpret_cast<volatile unsigned long long*>(D.sync_words) += 1;
+            __threadfence();
+        }
+    }
+}
+
+using dist_kern_t = void (*)(const SweepFactor, const SegDev, const SweepTileGeom, const SweepDistArgs);
+
+template <int P, bool PIV>
+dist_kern_t pick_nl(int NL) {
+    constexpr int KD = PIV ? 2 * P : P;
+    switch (NL) {
+    case 16: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, SWEEP_CH, 16>;
+    case 32: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, SWEEP_CH, 32>;
+    case 64: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, SWEEP_CH, 64>;
+    default: return nullptr;
+    }
+}
+
+dist_kern_t pick(int KL, bool piv, int NL) {
+    switch (KL) {
+    case 1: return piv ? pick_nl<1, true>(NL) : pick_nl<1, false>(NL);
+    case 2: return piv ? pick_nl<2, true>(NL) : pick_nl<2, false>(NL);
+    case 3: return piv ? pick_nl<3, true>(NL) : pick_nl<3, false>(NL);
+    case 4: return piv ? pick_nl<4, true>(NL) : pick_nl<4, false>(NL);
+    case 5: return piv ? pick_nl<5, true>(NL) : pick_nl<5, false>(NL);
+    default: return nullptr;
+    }
+}
+
+}  // namespace
+
+// 0: launched; -1: not eligible (the caller runs pass A / boundary kernels / pass B separately); else cudaError_t
+int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
+                      cudaStream_t st, bool dry_run) {
+    if (T.DF != 1 || T.DB != 1) return -1;                   // neighbours only
+    if (T.KL != F.KL || T.KD != F.KD) return -1;             // the slab's own factor needs the same kernel variant
+    if (G.in != G.out || G.sj_in != G.sj_out || G.s1_in != G.s1_out) return -1;  // in place
+    if (NL != 16 && NL != 32 && NL != 64) return -1;
+    const int NLt = NL / SWEEP_RL;
+    const int ncons = (NLt * F.SC + 31) / 32 * 32;
+    if (ncons > 288 || D.lag < 1 || D.lag > 16) return -1;
+    if ((uintptr_t) F.cfF % 16 != 0 || F.blob_doubles % 2 != 0) return -1;
+    SweepTileGeom Tg{};
+    Tg.in = G.in;
+    Tg.out = G.out;
+    Tg.L0 = G.L0;
+    Tg.L1 = G.L1;
+    Tg.s0_in = Tg.s0_out = G.s0_in;
+    Tg.s1_in = Tg.s1_out = G.s1_in;
+    Tg.nb0 = (G.L0 + NL - 1) / NL;
+    Tg.ntiles = Tg.nb0 * G.L1;
+    if (!dry_run)
+        if (int rc = sweep_strided_maps(G, F.n, NL, nullptr, nullptr, st, Tg)) return rc;
+    const int rows_needed = F.SC * SWEEP_CH + F.KL;
+    Tg.tile_doubles = (rows_needed * NL + 15) & ~15;
+    Tg.nbuf = DIST_NBUF;
+    const int KC = T.KD + T.KL, K = D.lag;
+    const size_t doubles = (size_t) 2 * DIST_NBUF * Tg.tile_doubles + (size_t) F.SC * (F.KL + F.KD) * NL + F.blob_doubles +
+                           ((F.n * KC + 1) & ~1) + ((T.KL * T.KL + 1) & ~1) + ((T.KD * T.KL + 1) & ~1) +
+                           (size_t) (K + 1) * T.KD * NL + (size_t) (2 * K + 1) * T.KL * NL + (size_t) T.KD * NL;
+    const size_t smem = doubles * 8 + (4 * DIST_NBUF + 1) * 8 + 64;
+    if (smem > 226 * 1024) return -1;
+    dist_kern_t k = pick(F.KL, F.piv != 0, NL);
+    if (!k) return -1;
+    if (dry_run) return 0;
+    cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    static int sms = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    int cap = (G.max_ctas > 0 && G.max_ctas < sms) ? G.max_ctas : sms;
+    if (cap > ADSB_DIST_MAX_CTAS) cap = ADSB_DIST_MAX_CTAS;
+    dim3 block(ncons + 64, 1, 1), grid(Tg.ntiles < cap ? Tg.ntiles : cap, 1, 1);
+    return (int) launch_ex(k, grid, block, smem, st, true, F, T, Tg, D);
+}
+
+}  // namespace adsb

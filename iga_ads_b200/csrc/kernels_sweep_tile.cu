@@ -29,22 +29,6 @@ namespace {
 
 constexpr int MAX_NBUF = 3;
 
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_addr(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
-                 "r"(c1), "r"(c2), "r"(smem_addr(src))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-
 // Block = ncons consumer threads (NLt lanes x chunks, padded to whole warps) + one producer warp.
 template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
 __global__ void __launch_bounds__(288, 1)
@@ -319,6 +303,54 @@ bool encode_tensor_map3(void* map, const double* base, const unsigned long long 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Tensor maps of the STRIDED tiles (NL x-values by n rows, one 3-D map per linear piece of the row-offset
+// tables, boxes of <= 256 rows), cached on the device; fills T.maps, T.nbox_*, T.row0_*, T.load_bytes.
+// 0: done; -1: this geometry cannot be moved by the TMA engine; otherwise a cudaError_t.
+int sweep_strided_maps(const SweepGeom& G, int n, int NL, const long long* off_in_h, const long long* off_out_h,
+                       cudaStream_t st, SweepTileGeom& T) {
+    auto even = [](long long v) { return (v & 1) == 0; };
+    const bool ptr_ok = ((uintptr_t) G.in % 16 == 0) && ((uintptr_t) G.out % 16 == 0);
+    if (!ptr_ok || G.s0_in != 1 || G.s0_out != 1 || (G.L1 > 1 && (!even(G.s1_in) || !even(G.s1_out)))) return -1;
+    std::vector<Box> bin, bout;
+    if (!cut_boxes(n, off_in_h, G.sj_in, bin) || !cut_boxes(n, off_out_h, G.sj_out, bout)) return -1;
+    for (const auto& b : bin)
+        if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+    for (const auto& b : bout)
+        if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+    T.nbox_in = (int) bin.size();
+    T.nbox_out = (int) bout.size();
+    T.load_bytes = 0;
+    std::vector<long long> key = {(long long) (uintptr_t) G.in, (long long) (uintptr_t) G.out, G.L0, G.L1, n, NL,
+                                  G.s1_in, G.s1_out};
+    for (size_t k = 0; k < bin.size(); ++k) {
+        T.row0_in[k] = bin[k].row0;
+        T.load_bytes += bin[k].rows * NL * 8;
+        key.insert(key.end(), {bin[k].row0, bin[k].rows, bin[k].off, bin[k].stride});
+    }
+    for (size_t k = 0; k < bout.size(); ++k) {
+        T.row0_out[k] = bout[k].row0;
+        key.insert(key.end(), {-1 - bout[k].row0, bout[k].rows, bout[k].off, bout[k].stride});
+    }
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it == g_map_cache.end()) {
+        std::vector<CUtensorMap> maps(bin.size() + bout.size());
+        for (size_t k = 0; k < bin.size(); ++k)
+            if (!make_map(&maps[k], G.in + bin[k].off, G.L0, bin[k].rows, G.L1, bin[k].stride, G.s1_in, NL)) return -1;
+        for (size_t k = 0; k < bout.size(); ++k)
+            if (!make_map(&maps[bin.size() + k], G.out + bout[k].off, G.L0, bout[k].rows, G.L1, bout[k].stride, G.s1_out, NL))
+                return -1;
+        void* d = nullptr;
+        if (cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return -1;
+        cudaError_t e = cudaMemcpyAsync(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `maps` is a local
+        if (e != cudaSuccess) return (int) e;
+        it = g_map_cache.emplace(std::move(key), d).first;
+    }
+    T.maps = it->second;
+    return 0;
+}
+
 // Returns cudaSuccess (0) when the tile kernel was launched, -1 when this sweep is not eligible (the
 // caller then uses the register-path kernel), or a CUDA error.
 int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
@@ -374,46 +406,8 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
         T.pitch = pitch;
         T.tile_doubles = NL * pitch;
     } else {
-        if (!ptr_ok || G.s0_in != 1 || G.s0_out != 1 || (G.L1 > 1 && (!even(G.s1_in) || !even(G.s1_out)))) return -1;
-        std::vector<Box> bin, bout;
-        if (!cut_boxes(F.n, off_in_h, G.sj_in, bin) || !cut_boxes(F.n, off_out_h, G.sj_out, bout)) return -1;
-        for (const auto& b : bin)
-            if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
-        for (const auto& b : bout)
-            if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+        if (int rc = sweep_strided_maps(G, F.n, NL, off_in_h, off_out_h, st, T)) return rc;
         T.tile_doubles = rows_needed * NL;
-        T.nbox_in = (int) bin.size();
-        T.nbox_out = (int) bout.size();
-        T.load_bytes = 0;
-        std::vector<long long> key = {(long long) (uintptr_t) G.in, (long long) (uintptr_t) G.out, G.L0, G.L1, F.n, NL,
-                                      G.s1_in, G.s1_out};
-        for (size_t k = 0; k < bin.size(); ++k) {
-            T.row0_in[k] = bin[k].row0;
-            T.load_bytes += bin[k].rows * NL * 8;
-            key.insert(key.end(), {bin[k].row0, bin[k].rows, bin[k].off, bin[k].stride});
-        }
-        for (size_t k = 0; k < bout.size(); ++k) {
-            T.row0_out[k] = bout[k].row0;
-            key.insert(key.end(), {-1 - bout[k].row0, bout[k].rows, bout[k].off, bout[k].stride});
-        }
-        std::lock_guard<std::mutex> lock(g_map_mutex);
-        auto it = g_map_cache.find(key);
-        if (it == g_map_cache.end()) {
-            std::vector<CUtensorMap> maps(bin.size() + bout.size());
-            for (size_t k = 0; k < bin.size(); ++k)
-                if (!make_map(&maps[k], G.in + bin[k].off, G.L0, bin[k].rows, G.L1, bin[k].stride, G.s1_in, NL)) return -1;
-            for (size_t k = 0; k < bout.size(); ++k)
-                if (!make_map(&maps[bin.size() + k], G.out + bout[k].off, G.L0, bout[k].rows, G.L1, bout[k].stride, G.s1_out,
-                              NL))
-                    return -1;
-            void* d = nullptr;
-            if (cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) return -1;
-            cudaError_t e = cudaMemcpyAsync(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `maps` is a local
-            if (e != cudaSuccess) return (int) e;
-            it = g_map_cache.emplace(std::move(key), d).first;
-        }
-        T.maps = it->second;
     }
     T.tile_doubles = (T.tile_doubles + 15) & ~15;  // 128 B granules
     const size_t fixed_doubles = (size_t) F.SC * (F.KL + F.KD) * NL + (size_t) F.blob_doubles;

@@ -40,6 +40,23 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_addr(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* map, int c0, int c1, int c2, const void* src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(smem_addr(src))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+
 // Programmatic dependent launch (griddepcontrol): a kernel launched with launch_ex(..., pdl = true) may start
 // while its predecessor in the stream is still draining -- its prologue (barrier init, staging of constant
 // tables) overlaps the predecessor's tail -- and must call pdl_wait() before it touches any memory the

@@ -164,6 +164,14 @@ class Context:
         check(self.lib.adsb_seg_sweep_view(self.h, axis, slot, seg, ctypes.c_void_p(in_ptr), ctypes.byref(vin),
                                            ctypes.c_void_p(out_ptr), ctypes.byref(vout)))
 
+    def dist_sweep_check(self, axis, slot, rank, view, nl, lag):
+        return check(self.lib.adsb_dist_sweep_check(self.h, axis, slot, rank, ctypes.byref(view), nl, lag)) == 1
+
+    def dist_sweep_view(self, axis, slot, data_ptr, view, args):
+        """fused distributed sweep of this rank's slab (args: _lib.DistArgs), in place"""
+        check(self.lib.adsb_dist_sweep_view(self.h, axis, slot, ctypes.c_void_p(data_ptr), ctypes.byref(view),
+                                            ctypes.byref(args)))
+
     @staticmethod
     def _ptr_list(ptrs):
         return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs]), len(ptrs)

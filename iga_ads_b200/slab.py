@@ -165,7 +165,8 @@ class SlabSim:
         f64 = dict(dtype=torch.float64, device=self.dev)
         S = world
         nhalo = (max(np.diff(self.bounds)) + 2 * p) * self.plane
-        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines)]
+        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines),
+                 ("flags", _lib.DIST_FLAGS)]   # 64-bit counters of the fused sweep (all-zero bits = 0)
         if peers is None and world > 1:
             peers = _SymmPeers(self, sizes)
             self.sym = {name: peers.local(name) for name, _ in sizes}
@@ -182,11 +183,50 @@ class SlabSim:
         if any(float(s.form.gamma) != 0.0 for s in self.substeps):
             self.ctx.load_tensor(1, False, FORCING)          # slab of the load tensor (context lo / cnt)
             self.forcing = self.ctx.device_ptr(FORCING)
+        # ---- fused distributed z sweep (one kernel per rank: pass A, exchange, pass B): every rank must agree
+        self.lag = int(os.environ.get("ADSB_SLAB_LAG", "4"))
+        rows = int(max(np.diff(self.bounds)))
+        sc = -(-rows // 18)
+        self.nl = 64
+        while self.nl > 16 and (self.nl // 2) * sc > 288:
+            self.nl //= 2
+        nl_env = int(os.environ.get("ADSB_SLAB_NL", "0"))
+        if nl_env in (16, 32, 64):
+            self.nl = nl_env
+        self.sync_words = torch.tensor([1, 0], dtype=torch.int64, device=self.dev)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.fused = False
+        self.want_fused = world > 1 and os.environ.get("ADSB_SLAB_FUSED", "1") != "0"
         self.cur = 0
         self.launches = 0
         self.exchange_bytes = 0
         self.timing, self._marks = False, []
         self.graph = None
+        self.stream = None   # virtual ranks: each rank's kernels run on its own stream
+        if self.want_fused and isinstance(self.peers, _SymmPeers):
+            self.agree_on_fused()
+
+    def fused_ok_locally(self):
+        """can this rank run the fused kernel for every z factor (chain depth 1, shared memory, kernel variant)?"""
+        if not self.want_fused:
+            return False
+        for slot in self.zslots:
+            while self.nl >= 16 and not self.ctx.dist_sweep_check(2, slot, self.rank, self._view_lines(self.cz), self.nl, self.lag):
+                self.nl //= 2
+            if self.nl < 16:
+                return False
+        return True
+
+    def agree_on_fused(self):
+        """real run: all ranks take the fused path only if every rank can, with the smallest nl any rank needs"""
+        import torch.distributed as dist
+
+        ok = self.fused_ok_locally()
+        t = self.torch.tensor([1 if ok else 0, self.nl if ok else 0], dtype=self.torch.int32, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        self.fused = bool(int(t[0].item()) == 1)
+        if self.fused:
+            self.nl = int(t[1].item())
 
     # ---- geometry helpers
     def _view(self, planes):
@@ -246,6 +286,47 @@ class SlabSim:
             dst = self.peers.tensor(r + 1, name)[0:p * pl]
             dst.copy_(mine[self.cz * pl:(self.cz + p) * pl], non_blocking=True)
             self.exchange_bytes += 8 * p * pl
+
+    def phase_fused(self, sub):
+        """fused path: right-hand side straight into the interior of the other state buffer, x and y sweeps in
+        place, then ONE kernel for the whole distributed z sweep (pass A, boundary exchange with the neighbours
+        through peer pointers and flags, pass B).  Call phase_finish afterwards."""
+        p, pl, nz = self.p, self.plane, self.n[2]
+        H = self.halo(self.cur)
+        out = self.interior(1 - self.cur).data_ptr()
+        lo, hi = max(0, self.z0 - p), min(nz, self.z0 + self.cz + p)
+        in_ptr = H.data_ptr() + 8 * (lo - self.z0 + p) * pl
+        v = self._view(self.cz)
+        self._mark("begin")
+        self.ctx.rhs_view(sub.form, in_ptr, self._view(hi - lo), [0, 0, lo], out, v, [0, 0, self.z0],
+                          forcing_ptr=self.forcing if float(sub.form.gamma) != 0.0 else None)
+        self._mark("rhs")
+        self.ctx.sweep_view(0, int(sub.slots[0]), out, v, out, v)
+        self._mark("sweep_x")
+        self.ctx.sweep_view(1, int(sub.slots[1]), out, v, out, v)
+        self._mark("sweep_y")
+        r, S = self.rank, self.world
+        a = _lib.DistArgs()
+        a.rank, a.nranks, a.nl, a.lag = r, S, self.nl, self.lag
+        a.sync_words = self.sync_words.data_ptr()
+        a.dseg_local, a.x_local = self.sym["dseg"].data_ptr(), self.sym["x"].data_ptr()
+        a.flags_local = self.sym["flags"].data_ptr()
+        a.dseg_next = self.peers.ptr(r + 1, "dseg") if r + 1 < S else None
+        a.flags_next = self.peers.ptr(r + 1, "flags") if r + 1 < S else None
+        a.x_prev = self.peers.ptr(r - 1, "x") if r > 0 else None
+        a.flags_prev = self.peers.ptr(r - 1, "flags") if r > 0 else None
+        a.error_flag = self.err_flag.data_ptr()
+        slot = int(sub.slots[2])
+        self.ctx.dist_sweep_view(2, slot, out, self._view_lines(self.cz), a)
+        seg = self.seg[slot]
+        self.exchange_bytes += 8 * self.lines * (seg["KL"] * (r + 1 < S) + seg["KD"] * (r > 0))
+        self.launches += 4
+        self._mark("sweep_z_fused")
+
+    def phase_finish(self, sub=None):
+        self.cur = 1 - self.cur
+        self.phase_publish(self.cur)
+        self._mark("halo")
 
     def phase_local(self, sub):
         """right-hand side, x and y sweeps, pass A of the z sweep, forward boundary values"""
@@ -324,6 +405,13 @@ class SlabSim:
         self.peers.barrier(1)
 
     def step(self):
+        if self.fused:
+            for sub in self.substeps:
+                self.phase_fused(sub)
+                self.phase_finish()
+                self.peers.barrier(0)   # the neighbours' boundary planes have landed in my halo regions
+                self._mark("barrier")
+            return
         for sub in self.substeps:
             self.phase_local(sub)
             self.peers.barrier(0)
@@ -375,9 +463,22 @@ class VirtualCluster:
     of the distributed path.  Peer stores land in ordinary tensors of the same process."""
 
     def __init__(self, problem, p, elements, dt, world, device=0):
+        import torch
+
         self.peers = _LocalPeers()
         self.ranks = [SlabSim(problem, p, elements, dt, r, world, device, peers=self.peers) for r in range(world)]
         self.n = self.ranks[0].n
+        # fused z sweep: the ranks' kernels wait for one another, so they must run CONCURRENTLY: one stream per
+        # rank and an SM cap that lets all of them be resident at once (the real run has a GPU per rank)
+        self.fused = world > 1 and all(s.fused_ok_locally() for s in self.ranks)
+        if self.fused:
+            nl = min(s.nl for s in self.ranks)
+            sms = torch.cuda.get_device_properties(device).multi_processor_count
+            for s in self.ranks:
+                s.fused, s.nl = True, nl
+                s.stream = torch.cuda.Stream(device=device)
+                s.ctx.set_stream(s.stream.cuda_stream)
+                s.ctx.set_sm_limit(max(1, sms // world))
 
     def set_state(self, full):
         nx, ny, nz = self.n
@@ -396,12 +497,25 @@ class VirtualCluster:
         return out.ravel()
 
     def step(self, nsteps=1):
+        torch = self.ranks[0].torch
         for _ in range(nsteps):
             for i in range(len(self.ranks[0].substeps)):
+                if self.fused:
+                    torch.cuda.synchronize()
+                    for s in self.ranks:
+                        with torch.cuda.stream(s.stream):
+                            s.phase_fused(s.substeps[i])
+                    torch.cuda.synchronize()
+                    for s in self.ranks:
+                        with torch.cuda.stream(s.stream):
+                            s.phase_finish()
+                    continue
                 for phase in SlabSim.PHASES:
                     for s in self.ranks:
                         getattr(s, phase)(s.substeps[i])
-        self.ranks[0].torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        if self.fused and any(int(s.err_flag.item()) for s in self.ranks):
+            raise RuntimeError("fused distributed sweep: a flag wait timed out")
 
 
 def gather_state(sim):

@@ -273,6 +273,36 @@ int adsb_seg_sweep_view(adsb_ctx* ctx, int axis, int slot, int seg, const double
  *   din:   din[s] = sum_{d=1..DF} Wf[s][d] Dseg[s-d];  X[s] = xhat_s[first KD rows] + XiF_s din[s]
  *   tin:   tin[s] = sum_{d=1..DB} Vb[s][d] X[s+d]       (skip when DB == 1: pass X to adsb_seg_correct_view)
  *   correct (pass B):  out = xhat + Psi tin[s] + Xi din[s]; in == out allowed. */
+/* The same, fused: pass A, the boundary exchange with the two neighbouring ranks and pass B in ONE persistent
+ * kernel per rank, software-pipelined tile by tile (csrc/kernels_sweep_dist.cu).  The slab is read from HBM
+ * once and written once; the boundary values travel as peer stores, ordered by per-CTA release/acquire flags
+ * that carry a launch epoch: sync_words[0] (device memory, set to 1 once by the caller; the kernel advances it,
+ * so a captured CUDA graph replays correctly), sync_words[1] = 0 is its scratch counter.  Every rank of the run
+ * must make the same sequence of calls with the same nl / lag / SM limit; chain depths DF = DB = 1 only (ADSB_ESTATE
+ * otherwise: use the separate entry points above).  In place on `data` (the rows of segment `rank`).
+ * state arrays: [S][K][lines] as above; flag arrays: ADSB_DIST_FLAGS 64-bit counters, zero-initialised once. */
+#define ADSB_DIST_FLAGS 512
+typedef struct {
+    int rank, nranks;
+    int nl;                          /* lines per tile: 16, 32 or 64 */
+    int lag;                         /* tiles between pass A and the exchange stages (0: default 4) */
+    unsigned long long* sync_words;  /* device: [0] epoch (initialise to 1), [1] 0 */
+    double* dseg_local;              /* own state arrays */
+    double* x_local;
+    double* dseg_next;               /* state array of rank + 1 (peer pointer; ignored on the last rank) */
+    double* x_prev;                  /* state array of rank - 1 (ignored on the first rank) */
+    unsigned long long* flags_local;
+    unsigned long long* flags_next;
+    unsigned long long* flags_prev;
+    int* error_flag;                 /* device int, set to 1 when a flag wait timed out (~2 s); may be NULL */
+} adsb_dist_args;
+int adsb_dist_sweep_view(adsb_ctx* ctx, int axis, int slot, double* data, const adsb_view* view,
+                         const adsb_dist_args* args);
+/* 1 when adsb_dist_sweep_view can run this slab shape with nl lines per tile and the given lag (shared memory,
+ * kernel variant, chain depths), 0 when not (use the separate entry points), < 0 on bad arguments.  Host only:
+ * lets every rank of a run agree on the path before anything is launched. */
+int adsb_dist_sweep_check(adsb_ctx* ctx, int axis, int slot, int rank, const adsb_view* view, int nl, int lag);
+
 int adsb_seg_dseg_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
                        const adsb_view* vin, double* const* dst, int ndst);
 int adsb_seg_din_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,

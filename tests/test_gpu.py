@@ -468,3 +468,86 @@ def test_slab_virtual_ranks_vs_oracle(oracle, problem, world, p, ne, dt):
         moved, _ = oracle.run(problem, p, ne, dt, steps, u0=np.nextafter(u0, u0 + sgn))
         tol = steps * max(TOL_STEP, FLOOR_ULPS * rel_l2(moved, want))
         assert rel_l2(cl.state(), want) < tol, (problem, world, steps, tol)
+
+
+@pytest.mark.parametrize("p,ne_z,world,nx,ny,lag,nl", [(2, 126, 2, 40, 24, 4, 16), (2, 190, 3, 70, 10, 2, 32),
+                                                      (3, 250, 2, 36, 20, 1, 64), (4, 388, 2, 34, 6, 3, 16),
+                                                      (2, 510, 8, 130, 9, 4, 64)])
+def test_fused_dist_sweep_equals_dgbtrs(oracle, p, ne_z, world, nx, ny, lag, nl):
+    """the ONE-kernel distributed z sweep (pass A + neighbour exchange through flags + pass B,
+    csrc/kernels_sweep_dist.cu): `world` ranks run concurrently on this GPU (a stream and an SM share each),
+    exchanging through peer pointers exactly as over NVLink; result == dgbtrs over the whole z lines.  Two
+    launches, so the device-side epoch is exercised."""
+    import torch
+
+    from iga_ads_b200 import host
+    from iga_ads_b200._lib import DIST_FLAGS, DistArgs, View
+
+    dev = torch.device("cuda", 0)
+    nz = ne_z + p
+    shape = (nx, ny, nz)
+    m = ads.matrix_1d(0, p, ne_z)
+    lu, piv = ads.band_factorize(m, p, p)
+    bounds = host.segment_bounds(piv, p, world)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    lines = nx * ny
+    ranks = []
+    for r in range(world):
+        ctx = ads.Context(shape)
+        ctx.set_factor(2, 0, lu, piv, p, p)
+        ctx.set_segments(2, 0, bounds, r, 1)
+        info = ctx.segment_info(2, 0)
+        assert (info["DF"], info["DB"]) == (1, 1)
+        st = torch.cuda.Stream()
+        ctx.set_stream(st.cuda_stream)
+        ctx.set_sm_limit(max(1, sms // world))
+        z0, cz = int(bounds[r]), int(bounds[r + 1] - bounds[r])
+        f64 = dict(dtype=torch.float64, device=dev)
+        ranks.append(dict(ctx=ctx, st=st, z0=z0, cz=cz, slab=torch.zeros(cz * lines, **f64),
+                          dseg=torch.zeros(world * info["KL"] * lines, **f64), x=torch.zeros(world * info["KD"] * lines, **f64),
+                          flags=torch.zeros(DIST_FLAGS, dtype=torch.int64, device=dev),
+                          sync=torch.tensor([1, 0], dtype=torch.int64, device=dev),
+                          err=torch.zeros(1, dtype=torch.int32, device=dev)))
+        v = View.make([nx, ny, cz], [1, nx, lines])
+        assert ctx.dist_sweep_check(2, 0, r, v, nl, lag)
+    for launch in range(2):
+        rhs = np.random.default_rng(17 + launch).standard_normal((nz, ny, nx))
+        zl = np.ascontiguousarray(np.moveaxis(rhs, 0, -1))
+        want = np.moveaxis(oracle.solve_factorized(lu, piv, p, p, zl).reshape(zl.shape), -1, 0)
+        for k in ranks:
+            k["slab"].copy_(torch.from_numpy(rhs[k["z0"]:k["z0"] + k["cz"]].copy()).reshape(-1))
+        torch.cuda.synchronize()
+        for r, k in enumerate(ranks):
+            a = DistArgs()
+            a.rank, a.nranks, a.nl, a.lag = r, world, nl, lag
+            a.sync_words = k["sync"].data_ptr()
+            a.dseg_local, a.x_local, a.flags_local = k["dseg"].data_ptr(), k["x"].data_ptr(), k["flags"].data_ptr()
+            if r + 1 < world:
+                a.dseg_next, a.flags_next = ranks[r + 1]["dseg"].data_ptr(), ranks[r + 1]["flags"].data_ptr()
+            if r > 0:
+                a.x_prev, a.flags_prev = ranks[r - 1]["x"].data_ptr(), ranks[r - 1]["flags"].data_ptr()
+            a.error_flag = k["err"].data_ptr()
+            k["ctx"].dist_sweep_view(2, 0, k["slab"].data_ptr(), View.make([nx, ny, k["cz"]], [1, nx, lines]), a)
+        torch.cuda.synchronize()
+        assert not any(int(k["err"].item()) for k in ranks), "flag wait timed out"
+        got = np.concatenate([k["slab"].cpu().numpy().reshape(k["cz"], ny, nx) for k in ranks])
+        assert rel_l2(got.ravel(), want.ravel()) < 1e-13, (launch, rel_l2(got.ravel(), want.ravel()))
+        assert all(int(k["sync"][0].item()) == 2 + launch for k in ranks)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_slab_cluster_fused_and_unfused_vs_oracle(oracle, monkeypatch, fused):
+    """heat_3d p=2 on 94^3 elements over 2 virtual ranks (48-plane slabs: neighbour-only chains), two steps: the
+    fused one-kernel z sweep and the separate pass A / boundary kernels / pass B must both match the oracle"""
+    from iga_ads_b200.slab import VirtualCluster
+
+    monkeypatch.setenv("ADSB_SLAB_FUSED", "1" if fused else "0")
+    p, ne, dt = 2, 94, 1e-7
+    n = ne + p
+    u0 = synthetic_state((n, n, n))
+    cl = VirtualCluster("heat_3d", p, ne, dt, 2)
+    assert cl.fused == fused
+    cl.set_state(u0)
+    cl.step(2)
+    want, _ = oracle.run("heat_3d", p, ne, dt, 2, u0=u0)
+    assert rel_l2(cl.state(), want) < 2 * TOL_STEP
