@@ -71,16 +71,25 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """starts nvidia-smi sampling every 50 ms and returns once the first sample has arrived (nvidia-smi takes a
+        moment to come up; a timed region of a few milliseconds would otherwise be over before it)"""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < wait_s:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """samples taken from here on count as `under load`"""
+        self.first = len(self.rows)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -92,7 +101,8 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        time.sleep(0.06)  # let the last sample of the loaded region arrive
+        for r in self.rows[self.first:] or self.rows[-1:]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -247,11 +257,24 @@ def run_single(args, cfg, local_rank):
     ctx.upload(U_PREV, u0)
 
     # ---- device-resident throughput
-    sim.advance(args.warmup)
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    sim.advance(args.warmup)
+    torch.cuda.synchronize()
+    # clocks under load: the timed region lasts only milliseconds, so the same steps keep running for ~0.3 s
+    # right before it (untimed, state is restored) while nvidia-smi samples; the timed steps follow back to back
+    sampler.mark()
+    t_load = time.time()
+    extra = 0
+    while time.time() - t_load < 0.3:
+        sim.advance(5)
+        extra += 5
+        torch.cuda.synchronize()
+    ctx.upload(U, u0)
+    ctx.upload(U_PREV, u0)
+    warm = args.warmup + (args.warmup & 1)   # even, as the multi-GPU leg needs it: the checksums stay comparable
+    sim.advance(warm)
+    torch.cuda.synchronize()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -264,7 +287,7 @@ def run_single(args, cfg, local_rank):
     clocks = sampler.stop()
     value = N * args.steps / (ms * 1e-3)
     final = ctx.download(U)
-    checksum = {"steps": args.warmup + args.steps, "sum": float(final.sum()), "l2": float(np.linalg.norm(final))}
+    checksum = {"steps": warm + args.steps, "sum": float(final.sum()), "l2": float(np.linalg.norm(final))}
     state_ok = bool(np.isfinite(final).all())
     del final
 

@@ -64,12 +64,19 @@ class View(ctypes.Structure):
 
 class DistArgs(ctypes.Structure):
     """adsb_dist_args (include/adsb200.h): one rank's arguments of the fused distributed sweep"""
-    _fields_ = [("rank", c_int), ("nranks", c_int), ("nl", c_int), ("lag", c_int), ("sync_words", vp),
-                ("dseg_local", vp), ("x_local", vp), ("dseg_next", vp), ("x_prev", vp),
-                ("flags_local", vp), ("flags_next", vp), ("flags_prev", vp), ("error_flag", vp)]
+    _fields_ = [("rank", c_int), ("nranks", c_int), ("nl", c_int), ("lag", c_int),
+                ("dseg_local", vp), ("x_local", vp), ("dseg_next", vp), ("x_prev", vp), ("error_flag", vp)]
 
 
-DIST_FLAGS = 512
+DIST_SENTINEL_WORD = 0x7FF7A5A5   # both 32-bit halves of the sentinel the fused sweep's state arrays hold
+
+
+def fill_sentinel(t):
+    """fill a float64 torch tensor (a state array of the fused distributed sweep) with the sentinel"""
+    import torch
+
+    t.view(torch.int32).fill_(DIST_SENTINEL_WORD)
+
 
 _SIGNATURES = {
     # name: (restype, argtypes)

@@ -1032,12 +1032,13 @@ int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const ad
     SegSet* g;
     if (int rc = seg_of(c, axis, slot, &g)) return rc;
     if (!data || !v || !d) return fail(ADSB_EINVAL, "dist_sweep_view: null argument");
-    static_assert(ADSB_DIST_FLAGS == 2 * ADSB_DIST_MAX_CTAS, "flag array size out of sync");
+    static_assert(ADSB_DIST_SENTINEL_WORD == (unsigned) (ADSB_DIST_SENTINEL_BITS >> 32) &&
+                      ADSB_DIST_SENTINEL_WORD == (unsigned) (ADSB_DIST_SENTINEL_BITS & 0xffffffffu),
+                  "sentinel constants out of sync");
     if (d->rank < g->local_lo || d->rank >= g->local_lo + g->local_cnt || d->nranks != g->dev.S)
         return fail(ADSB_EINVAL, "dist_sweep_view: rank is not a local segment of this context");
-    if (!d->dseg_local || !d->x_local || !d->flags_local || !d->sync_words || (d->rank > 0 && (!d->x_prev || !d->flags_prev)) ||
-        (d->rank + 1 < d->nranks && (!d->dseg_next || !d->flags_next)))
-        return fail(ADSB_EINVAL, "dist_sweep_view: missing state / flag arrays");
+    if (!d->dseg_local || !d->x_local || (d->rank > 0 && !d->x_prev) || (d->rank + 1 < d->nranks && !d->dseg_next))
+        return fail(ADSB_EINVAL, "dist_sweep_view: missing state arrays");
     if (int rc = select_device(c)) return rc;
     const SweepFactor& F = g->local[d->rank - g->local_lo];
     if (v->n[axis] != F.n) return fail(ADSB_EINVAL, "dist_sweep_view: the view does not span the slab");
@@ -1057,14 +1058,10 @@ int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const ad
     D.rank = d->rank;
     D.row_base = g->bounds[d->rank];
     D.lag = d->lag > 0 ? d->lag : 4;
-    D.sync_words = d->sync_words;
     D.dseg_local = d->dseg_local;
     D.x_local = d->x_local;
     D.dseg_next = d->rank + 1 < d->nranks ? d->dseg_next : nullptr;
     D.x_prev = d->rank > 0 ? d->x_prev : nullptr;
-    D.flags_local = d->flags_local;
-    D.flags_next = d->rank + 1 < d->nranks ? d->flags_next : nullptr;
-    D.flags_prev = d->rank > 0 ? d->flags_prev : nullptr;
     D.error_flag = d->error_flag;
     StageTimer t(c, 1 + axis);
     const int rc = launch_sweep_dist(F, g->dev, G, D, d->nl, c->stream);

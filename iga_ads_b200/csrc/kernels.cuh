@@ -204,20 +204,15 @@ int launch_seg_tin(const SegDev& T, int s_lo, int s_hi, long long L, const doubl
 int launch_seg_correct(const SegDev& T, const SegGeom& G, const double* din, const double* tin, int tin_is_x,
                        int max_rows, cudaStream_t st);
 
-// Fused distributed sweep (kernels_sweep_dist.cu): one rank's arguments.  State arrays are [S][K][lines];
-// flag arrays hold 2 * ADSB_DIST_MAX_CTAS counters (forward values from the previous rank, backward values from
-// the next one), one per CTA.
-constexpr int ADSB_DIST_MAX_CTAS = 256;
+// Fused distributed sweep (kernels_sweep_dist.cu): one rank's arguments.  State arrays are [S][K][lines] and
+// hold ADSB_DIST_SENTINEL_BITS in every word between sweeps (the exchange protocol polls the data itself).
+constexpr unsigned long long ADSB_DIST_SENTINEL_BITS = 0x7FF7A5A57FF7A5A5ull;  // a signalling NaN, both halves equal
 struct SweepDistArgs {
     int rank, row_base, lag;
-    unsigned long long* sync_words;  // [0] launch epoch (>= 1), [1] CTAs finished in the running launch
     double* dseg_local;
     double* x_local;
     double* dseg_next;  // state array of rank + 1 (peer pointer), nullptr on the last rank
     double* x_prev;     // state array of rank - 1, nullptr on the first rank
-    unsigned long long* flags_local;
-    unsigned long long* flags_next;
-    unsigned long long* flags_prev;
     int* error_flag;
 };
 // dry_run: only report eligibility (0 / -1), launch nothing

@@ -10,18 +10,22 @@
 //
 //   iteration i of a CTA (tile sequence identical on all ranks, CTA b pairs with CTA b of the neighbours):
 //     A (tile i)       TMA load, local substitution in shared memory, TMA store of xhat in place;
-//                      Dseg = E * xhat[last KL rows] stored into the NEXT rank's state array, then a
-//                      release flag on that rank ("tile i of CTA b: forward values are there")
-//     B1 (tile i-K)    wait for the PREVIOUS rank's flag, din <- its Dseg; X = xhat[first KD rows] + XiF din
-//                      stored into the previous rank's state array + flag
-//     B2 (tile i-2K)   wait for the NEXT rank's flag, tin <- its X; the tile comes back by TMA (an L2 hit: it
-//                      was stored 2K tiles ago), x += Psi tin + Xi din in shared memory, TMA store in place
+//                      Dseg = E * xhat[last KL rows] stored into the NEXT rank's state array
+//     B1 (tile i-K)    din <- the PREVIOUS rank's Dseg (polled, see below); X = xhat[first KD rows] + XiF din
+//                      stored into the previous rank's state array
+//     B2 (tile i-2K)   tin <- the NEXT rank's X (polled); the tile comes back by TMA (an L2 hit: it was stored
+//                      2K tiles ago), x += Psi tin + Xi din in shared memory, TMA store in place
 //
-// so the NVLink round trips (a few microseconds) hide behind K tiles of work, the slab is read from HBM once
-// and written once (16 B/DOF: the intermediate xhat lives in L2 -- 2K tiles per CTA, tens of MB in all), and no
+// so the NVLink latency (a few microseconds) hides behind K tiles of work, the slab is read from HBM once and
+// written once (16 B/DOF: the intermediate xhat lives in L2 -- 2K tiles per CTA, tens of MB in all), and no
 // host-side barrier separates the stages.  Two producer warps feed the two tile rings; the consumer warps run
-// A, B1, B2 back to back.  Flags carry the launch epoch, so they never need resetting; the epoch is a device
-// counter advanced by the last CTA to finish (a replayed CUDA graph cannot carry it as a kernel argument).
+// A, B1, B2 back to back.
+//
+// Exchange protocol: the boundary values validate themselves.  Every word of the state arrays holds a sentinel
+// (one particular signalling-NaN bit pattern, ADSB_DIST_SENTINEL) until the neighbour's 8-byte store replaces
+// it; the receiver polls the word it needs with volatile loads, takes the value and puts the sentinel back
+// for the next sweep.  No flags, no fences, no epochs: a first version that published per-tile flags behind
+// __threadfence_system() spent 20 us per tile waiting for the fences to drain the SM's TMA traffic.
 #include <cuda.h>
 
 #include <cstdint>
@@ -36,31 +40,27 @@ namespace {
 
 constexpr int DIST_NBUF = 2;  // slots per tile ring
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+// Take one boundary value out of the inbox: spin until the neighbour's store has replaced the sentinel, put the
+// sentinel back.  Gives up after ~2 s (sets *err; the result is then garbage but nothing hangs).
+__device__ __forceinline__ double take_value(double* slot, int* err) {
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(slot);
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_volatile(const double* p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-// spin until *flag >= want; gives up after ~2 s (sets *err, the results are then garbage but nothing hangs)
-__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long want, int* err) {
-    long long t0 = clock64();
-    unsigned ns = 20;
-    while (ld_acquire_sys(flag) < want) {
-        __nanosleep(ns);
-        if (ns < 400) ns *= 2;
-        if (clock64() - t0 > 4000000000ll) {
-            if (err) atomicExch(err, 1);
-            break;
-        }
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+    if (v == ADSB_DIST_SENTINEL_BITS) {
+        const long long t0 = clock64();
+        unsigned ns = 32;
+        do {
+            __nanosleep(ns);
+            if (ns < 512) ns *= 2;
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (clock64() - t0 > 4000000000ll) {
+                if (err) atomicExch(err, 1);
+                break;
+            }
+        } while (v == ADSB_DIST_SENTINEL_BITS);
     }
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w), "l"(ADSB_DIST_SENTINEL_BITS) : "memory");
+    return __longlong_as_double((long long) v);
 }
 
 template <int KL, int KD, bool PIV, int CH, int NL>
@@ -213,12 +213,6 @@ __global__ void __launch_bounds__(352, 1)
     const int c = min(craw, SC - 1);  // padding threads shadow the last chunk in pass A (identical values)
     const int j0 = c * CH;
     const long long L = (long long) G.L0 * G.L1;
-    // launch epoch: every CTA reads it before the last one to finish can advance it
-    const unsigned long long base = *reinterpret_cast<volatile unsigned long long*>(D.sync_words) << 32;
-    unsigned long long* flagA_in = D.flags_local + blockIdx.x;                         // written by rank r-1
-    unsigned long long* flagB_in = D.flags_local + ADSB_DIST_MAX_CTAS + blockIdx.x;    // written by rank r+1
-    unsigned long long* flagA_out = D.flags_next ? D.flags_next + blockIdx.x : nullptr;
-    unsigned long long* flagB_out = D.flags_prev ? D.flags_prev + ADSB_DIST_MAX_CTAS + blockIdx.x : nullptr;
 
     for (int it = 0; it < my_count + 2 * K; ++it) {
         // ================================================================== A: tile it
@@ -262,13 +256,9 @@ __global__ void __launch_bounds__(352, 1)
                         D.dseg_next[((size_t) r * KL + kk) * L + line0 + ln] = acc;
                     }
                 }
-                __threadfence_system();
             }
             sweep_sync(ncons);
-            if (tid == 0) {
-                mbar_arrive(&doneA[b]);
-                if (flagA_out) st_release_sys(flagA_out, base + (unsigned long long) it + 1);
-            }
+            if (tid == 0) mbar_arrive(&doneA[b]);
         }
         // ================================================================== B1: tile it - K
         const int j1 = it - K;
@@ -278,13 +268,9 @@ __global__ void __launch_bounds__(352, 1)
             const long long line0 = (long long) bx * NL + (long long) m * G.L0;
             const int lanes = min(NL, G.L0 - bx * NL);
             double* dn = s_din + (size_t) (j1 % (2 * K + 1)) * KL * NL;
-            if (r > 0) {
-                if (tid == 0) wait_flag(flagA_in, base + (unsigned long long) j1 + 1, D.error_flag);
-                sweep_sync(ncons);
-            }
             for (int i = tid; i < KL * NL; i += ncons) {
                 const int kk = i / NL, ln = i % NL;
-                dn[i] = (r > 0 && ln < lanes) ? ld_volatile(D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + line0 + ln) : 0.0;
+                dn[i] = (r > 0 && ln < lanes) ? take_value(D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + line0 + ln, D.error_flag) : 0.0;
             }
             sweep_sync(ncons);
             if (D.x_prev) {
@@ -298,9 +284,6 @@ __global__ void __launch_bounds__(352, 1)
                         D.x_prev[((size_t) r * KD + ii) * L + line0 + ln] = acc;
                     }
                 }
-                __threadfence_system();
-                sweep_sync(ncons);
-                if (tid == 0) st_release_sys(flagB_out, base + (unsigned long long) j1 + 1);
             }
         }
         // ================================================================== B2: tile it - 2K
@@ -313,13 +296,9 @@ __global__ void __launch_bounds__(352, 1)
             const int b = j2 % DIST_NBUF;
             double* tile = ringD + (size_t) b * tile_doubles;
             const double* dn = s_din + (size_t) (j2 % (2 * K + 1)) * KL * NL;
-            if (r + 1 < S) {
-                if (tid == 0) wait_flag(flagB_in, base + (unsigned long long) j2 + 1, D.error_flag);
-                sweep_sync(ncons);
-            }
             for (int i = tid; i < KD * NL; i += ncons) {
                 const int ii = i / NL, ln = i % NL;
-                s_tin[i] = (r + 1 < S && ln < lanes) ? ld_volatile(D.x_local + ((size_t) (r + 1) * KD + ii) * L + line0 + ln) : 0.0;
+                s_tin[i] = (r + 1 < S && ln < lanes) ? take_value(D.x_local + ((size_t) (r + 1) * KD + ii) * L + line0 + ln, D.error_flag) : 0.0;
             }
             mbar_wait(&fullD[b], (uint32_t) ((j2 / DIST_NBUF) & 1));
             sweep_sync(ncons);
@@ -347,15 +326,6 @@ __global__ void __launch_bounds__(352, 1)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             sweep_sync(ncons);
             if (tid == 0) mbar_arrive(&doneD[b]);
-        }
-    }
-    if (tid == 0) {
-        unsigned int* done_ctas = reinterpret_cast<unsigned int*>(D.sync_words + 1);
-        __threadfence();
-        if (atomicAdd(done_ctas, 1u) == gridDim.x - 1) {
-            *done_ctas = 0;
-            *reinterpret_cast<volatile unsigned long long*>(D.sync_words) += 1;
-            __threadfence();
         }
     }
 }
@@ -429,7 +399,6 @@ int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G,
         return v;
     }();
     int cap = (G.max_ctas > 0 && G.max_ctas < sms) ? G.max_ctas : sms;
-    if (cap > ADSB_DIST_MAX_CTAS) cap = ADSB_DIST_MAX_CTAS;
     dim3 block(ncons + 64, 1, 1), grid(Tg.ntiles < cap ? Tg.ntiles : cap, 1, 1);
     return (int) launch_ex(k, grid, block, smem, st, true, F, T, Tg, D);
 }

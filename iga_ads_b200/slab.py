@@ -53,7 +53,15 @@ class _SelfPeers(_LocalPeers):
     own arrays (results are meaningless, the work per kernel is that of a real rank)."""
 
     def ptr(self, rank, name):
-        return self.ranks[0].sym[name].data_ptr()
+        me = self.ranks[0]
+        base = me.sym[name].data_ptr()
+        # loop the exchange of the fused sweep back: what the rank stores for its neighbours (its own slot of their
+        # state arrays) must land where it expects THEIR values (slots rank -/+ 1 of its own arrays)
+        if name == "dseg":
+            return base - 8 * me.KL * me.lines
+        if name == "x":
+            return base + 8 * me.KD * me.lines
+        return base
 
     def tensor(self, rank, name):
         return self.ranks[0].sym[name]
@@ -165,8 +173,7 @@ class SlabSim:
         f64 = dict(dtype=torch.float64, device=self.dev)
         S = world
         nhalo = (max(np.diff(self.bounds)) + 2 * p) * self.plane
-        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines),
-                 ("flags", _lib.DIST_FLAGS)]   # 64-bit counters of the fused sweep (all-zero bits = 0)
+        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines)]
         if peers is None and world > 1:
             peers = _SymmPeers(self, sizes)
             self.sym = {name: peers.local(name) for name, _ in sizes}
@@ -193,7 +200,6 @@ class SlabSim:
         nl_env = int(os.environ.get("ADSB_SLAB_NL", "0"))
         if nl_env in (16, 32, 64):
             self.nl = nl_env
-        self.sync_words = torch.tensor([1, 0], dtype=torch.int64, device=self.dev)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.fused = False
         self.want_fused = world > 1 and os.environ.get("ADSB_SLAB_FUSED", "1") != "0"
@@ -224,9 +230,17 @@ class SlabSim:
         ok = self.fused_ok_locally()
         t = self.torch.tensor([1 if ok else 0, self.nl if ok else 0], dtype=self.torch.int32, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        self.fused = bool(int(t[0].item()) == 1)
-        if self.fused:
+        if int(t[0].item()) == 1:
             self.nl = int(t[1].item())
+            self.enable_fused()
+            self.peers.barrier(0)   # every inbox holds the sentinel before any neighbour stores into it
+
+    def enable_fused(self):
+        """the fused kernel's exchange protocol: every word of the state arrays holds a sentinel until the
+        neighbour's store replaces it (see csrc/kernels_sweep_dist.cu)"""
+        self.fused = True
+        _lib.fill_sentinel(self.sym["dseg"])
+        _lib.fill_sentinel(self.sym["x"])
 
     # ---- geometry helpers
     def _view(self, planes):
@@ -308,13 +322,9 @@ class SlabSim:
         r, S = self.rank, self.world
         a = _lib.DistArgs()
         a.rank, a.nranks, a.nl, a.lag = r, S, self.nl, self.lag
-        a.sync_words = self.sync_words.data_ptr()
         a.dseg_local, a.x_local = self.sym["dseg"].data_ptr(), self.sym["x"].data_ptr()
-        a.flags_local = self.sym["flags"].data_ptr()
         a.dseg_next = self.peers.ptr(r + 1, "dseg") if r + 1 < S else None
-        a.flags_next = self.peers.ptr(r + 1, "flags") if r + 1 < S else None
         a.x_prev = self.peers.ptr(r - 1, "x") if r > 0 else None
-        a.flags_prev = self.peers.ptr(r - 1, "flags") if r > 0 else None
         a.error_flag = self.err_flag.data_ptr()
         slot = int(sub.slots[2])
         self.ctx.dist_sweep_view(2, slot, out, self._view_lines(self.cz), a)
@@ -475,7 +485,8 @@ class VirtualCluster:
             nl = min(s.nl for s in self.ranks)
             sms = torch.cuda.get_device_properties(device).multi_processor_count
             for s in self.ranks:
-                s.fused, s.nl = True, nl
+                s.nl = nl
+                s.enable_fused()
                 s.stream = torch.cuda.Stream(device=device)
                 s.ctx.set_stream(s.stream.cuda_stream)
                 s.ctx.set_sm_limit(max(1, sms // world))

@@ -81,13 +81,22 @@ def run_multi_gpu_bench(args, cfg, rank, world, local_rank):
     host = torch.from_numpy(u0).pin_memory()
     sim.set_local_state(host.numpy())
     sim.publish()
-    sim.advance(args.warmup)
-    torch.cuda.synchronize()
-    dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    sim.advance(args.warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    # clocks under load: keep stepping ~0.3 s (untimed) while nvidia-smi samples, then restore the state
+    sampler.mark()
+    for _ in range(60 if world >= 4 else 30):
+        sim.advance(10)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sim.cur = 0
+    sim.set_local_state(host.numpy())
+    sim.publish()
+    sim.advance(args.warmup + (args.warmup & 1))
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -107,7 +116,10 @@ def run_multi_gpu_bench(args, cfg, rank, world, local_rank):
     fin = red[2:3].clone()
     dist.all_reduce(red[:2], op=dist.ReduceOp.SUM)
     dist.all_reduce(fin, op=dist.ReduceOp.MIN)
-    checksum = {"steps": args.warmup + args.steps, "sum": float(red[0].item()), "l2": float(red[1].sqrt().item())}
+    warm = args.warmup + (args.warmup & 1)
+    checksum = {"steps": warm + args.steps, "sum": float(red[0].item()), "l2": float(red[1].sqrt().item())}
+    errf = sim.err_flag.clone().to(torch.float64)
+    dist.all_reduce(errf, op=dist.ReduceOp.MAX)
     finite = bool(fin.item() == 1.0)
     # per-phase device times of rank 0 (separate eager pass, events between the launches)
     sim.timing = True
@@ -155,7 +167,10 @@ def run_multi_gpu_bench(args, cfg, rank, world, local_rank):
                                       "neighbours, pass B); p halo planes per step; nothing is transposed",
                        "exchange": f"{seg['KL']} + {seg['KD']} doubles per z line and rank boundary (chain depth "
                                    f"{seg['DF']}/{seg['DB']}) stored by the kernels through peer pointers (symmetric "
-                                   "memory), halo planes by the copy engines, 3 signal barriers per sub-step",
+                                   "memory), halo planes by the copy engines; " +
+                                   (f"ONE fused kernel per rank for the z sweep (pass A, flag-ordered neighbour exchange, "
+                                    f"pass B; {sim.nl} lines per tile, lag {sim.lag}), 1 signal barrier per sub-step"
+                                    if sim.fused else "pass A / boundary kernels / pass B, 3 signal barriers per sub-step"),
                        "cuda_graph": bool(sim.graph is not None)},
             "roofline": {"bound": "hbm", "kernel": "whole step, per GPU (64 B/DOF algorithmic; the distributed z sweep "
                                                    "itself moves 32 B/DOF)", "achieved": achieved,
@@ -163,7 +178,7 @@ def run_multi_gpu_bench(args, cfg, rank, world, local_rank):
                          "exchange_bytes_per_gpu_step": timed_exchange / max(args.steps, 1),
                          "phase_ms_rank0": phases},
             "clocks": clocks, "gpu_launches": timed_launches * world, "finite": finite, "checksum": checksum,
-            "parity": parity,
+            "parity": parity, "flag_wait_timeouts": bool(errf.item() > 0),
         }
         if e2e:
             line["e2e"] = e2e

@@ -275,26 +275,24 @@ int adsb_seg_sweep_view(adsb_ctx* ctx, int axis, int slot, int seg, const double
  *   correct (pass B):  out = xhat + Psi tin[s] + Xi din[s]; in == out allowed. */
 /* The same, fused: pass A, the boundary exchange with the two neighbouring ranks and pass B in ONE persistent
  * kernel per rank, software-pipelined tile by tile (csrc/kernels_sweep_dist.cu).  The slab is read from HBM
- * once and written once; the boundary values travel as peer stores, ordered by per-CTA release/acquire flags
- * that carry a launch epoch: sync_words[0] (device memory, set to 1 once by the caller; the kernel advances it,
- * so a captured CUDA graph replays correctly), sync_words[1] = 0 is its scratch counter.  Every rank of the run
- * must make the same sequence of calls with the same nl / lag / SM limit; chain depths DF = DB = 1 only (ADSB_ESTATE
- * otherwise: use the separate entry points above).  In place on `data` (the rows of segment `rank`).
- * state arrays: [S][K][lines] as above; flag arrays: ADSB_DIST_FLAGS 64-bit counters, zero-initialised once. */
-#define ADSB_DIST_FLAGS 512
+ * once and written once; the boundary values travel as 8-byte peer stores that validate themselves: every word
+ * of the state arrays holds a sentinel (the 32-bit pattern ADSB_DIST_SENTINEL_WORD twice: a signalling NaN)
+ * until the neighbour's store replaces it; the receiver polls the word, takes it and puts the sentinel back.
+ * The caller fills both state arrays with the sentinel ONCE (e.g. a 32-bit memset of the word) and separates
+ * consecutive sweeps on the same arrays by a barrier over the ranks (the end-of-step halo barrier does).
+ * Every rank must make the same sequence of calls with the same nl / lag / SM limit; chain depths DF = DB = 1
+ * only (ADSB_ESTATE otherwise: use the separate entry points above).  In place on `data` (the rows of segment
+ * `rank`).  state arrays: [S][K][lines] as above. */
+#define ADSB_DIST_SENTINEL_WORD 0x7FF7A5A5u
 typedef struct {
     int rank, nranks;
     int nl;                          /* lines per tile: 16, 32 or 64 */
     int lag;                         /* tiles between pass A and the exchange stages (0: default 4) */
-    unsigned long long* sync_words;  /* device: [0] epoch (initialise to 1), [1] 0 */
-    double* dseg_local;              /* own state arrays */
+    double* dseg_local;              /* own state arrays, sentinel-filled */
     double* x_local;
     double* dseg_next;               /* state array of rank + 1 (peer pointer; ignored on the last rank) */
     double* x_prev;                  /* state array of rank - 1 (ignored on the first rank) */
-    unsigned long long* flags_local;
-    unsigned long long* flags_next;
-    unsigned long long* flags_prev;
-    int* error_flag;                 /* device int, set to 1 when a flag wait timed out (~2 s); may be NULL */
+    int* error_flag;                 /* device int, set to 1 when a poll timed out (~2 s); may be NULL */
 } adsb_dist_args;
 int adsb_dist_sweep_view(adsb_ctx* ctx, int axis, int slot, double* data, const adsb_view* view,
                          const adsb_dist_args* args);

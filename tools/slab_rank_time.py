@@ -17,7 +17,8 @@ from iga_ads_b200.slab import SlabSim, _SelfPeers  # noqa: E402
 
 def run(world, rank, problem="heat_3d", p=2, ne=512, steps=6):
     sim = SlabSim(problem, p, ne, 1e-7 if problem == "heat_3d" else 1e-6, rank, world, 0, peers=_SelfPeers())
-    sim.fused = sim.fused_ok_locally()   # loop-back peers: the rank's flags and state arrays stand in for its neighbours'
+    if sim.fused_ok_locally():   # loop-back peers: the rank's own state arrays stand in for its neighbours'
+        sim.enable_fused()
     rng = np.random.default_rng(0)
     sim.set_local_state(rng.standard_normal(sim.cz * sim.n[1] * sim.n[0]))
     for _ in range(3):
