@@ -980,7 +980,8 @@ int adsb_set_axis_segments(adsb_ctx* c, int axis, int slot, int nseg, const int*
         std::vector<int> ip(D.ipiv.begin() + a, D.ipiv.begin() + b);
         for (int& v : ip) v -= a;
         SweepPlan L;
-        if (int rc = build_sweep_plan(b - a, D.kl, D.ku, D.ldab, D.ab.data() + (size_t) a * D.ldab, ip.data(), SWEEP_CH, 1, L))
+        if (int rc = build_sweep_plan(b - a, D.kl, D.ku, D.ldab, D.ab.data() + (size_t) a * D.ldab, ip.data(), SWEEP_CH, 1, L,
+                                      P.piv != 0))
             return rc;
         if (int rc = upload_plan(L, g.local[i], g.allocs)) return rc;
     }

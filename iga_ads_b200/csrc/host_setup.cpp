@@ -298,9 +298,10 @@ double maxabs(const double* A, int count) {
 }  // namespace
 
 int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch, int group,
-                     SweepPlan& P) {
+                     SweepPlan& P, bool force_piv) {
     const int kd = kl + ku;
-    bool piv = false;
+    bool piv = force_piv;  // a slab of a factor with row interchanges uses the interchange variant even if its own
+                           // columns have none, so that every slab runs the same kernel and state widths
     for (int j = 0; j < n; ++j) {
         int t = ipiv[j] - 1 - j;
         if (t < 0 || t > kl || j + t >= n) return fail(ADSB_EINVAL, "factor: bad pivot vector");

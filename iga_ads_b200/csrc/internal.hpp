@@ -37,7 +37,7 @@ struct SweepPlan {
     std::vector<double> V;       // [SC][MAX_DEPTH-1][KD][KD]  V_{c,d}, d = 2..  (products of Rm)
 };
 int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, int ch, int group,
-                     SweepPlan& plan);
+                     SweepPlan& plan, bool force_piv = false);
 
 // Segmented substitution (host_setup.cpp): a line is cut into S segments [bounds[s], bounds[s+1]); every
 // segment is solved on its own (the same factor restricted to the segment, zero incoming states) and the

@@ -18,8 +18,8 @@
 //
 // so the NVLink latency (a few microseconds) hides behind K tiles of work, the slab is read from HBM once and
 // written once (16 B/DOF: the intermediate xhat lives in L2 -- 2K tiles per CTA, tens of MB in all), and no
-// host-side barrier separates the stages.  Two producer warps feed the two tile rings; the consumer warps run
-// A, B1, B2 back to back.
+// host-side barrier separates the stages.  Warp roles: group A (pass A), group B (boundary values and pass B,
+// so the latency of polling the neighbours overlaps pass A of later tiles), two producer warps (one per ring).
 //
 // Exchange protocol: the boundary values validate themselves.  Every word of the state arrays holds a sentinel
 // (one particular signalling-NaN bit pattern, ADSB_DIST_SENTINEL) until the neighbour's 8-byte store replaces
@@ -63,13 +63,22 @@ __device__ __forceinline__ double take_value(double* slot, int* err) {
     return __longlong_as_double((long long) v);
 }
 
+constexpr int DIST_NB = 128;  // threads of the B group (boundary values + pass B)
+
+__device__ __forceinline__ void group_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Thread roles: [0, ncons) group A (pass A: lanes x chunks, as in sweep_tile_kernel), [ncons, ncons + 128) group B
+// (boundary values and pass B), then two producer warps (ring A, ring D).  The groups meet only through
+// mbarriers: group A hands the first KD rows of every finished tile to group B through a small ring.
 template <int KL, int KD, bool PIV, int CH, int NL>
-__global__ void __launch_bounds__(352, 1)
+__global__ void __launch_bounds__(384, 1)
     sweep_dist_kernel(const SweepFactor F0, const SegDev T, const SweepTileGeom G, const SweepDistArgs D) {
-    constexpr int RL = SWEEP_RL, NLt = NL / RL, KC = KD + KL;
+    constexpr int RL = SWEEP_RL, NLt = NL / RL, KC = KD + KL, NB = DIST_NB;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int SC = F0.SC, n = F0.n;
-    const int ncons = (int) blockDim.x - 64;
+    const int ncons = (int) blockDim.x - NB - 64;
     const int tid = threadIdx.x;
     const int tile_doubles = G.tile_doubles;
     const int K = D.lag;
@@ -82,15 +91,17 @@ __global__ void __launch_bounds__(352, 1)
     double* s_cf = s_tab + F0.blob_doubles;                   // [n][KC]   Psi | Xi of the slab's rows
     double* s_E = s_cf + ((n * KC + 1) & ~1);                 // [KL][KL]
     double* s_XiF = s_E + ((KL * KL + 1) & ~1);               // [KD][KL]
-    double* s_xf = s_XiF + ((KD * KL + 1) & ~1);              // [K+1][KD][NL]   xhat first rows of tiles between A and B1
-    double* s_din = s_xf + (K + 1) * KD * NL;                 // [2K+1][KL][NL]  din of tiles between B1 and B2
-    double* s_tin = s_din + (2 * K + 1) * KL * NL;            // [KD][NL]
+    double* s_xf = s_XiF + ((KD * KL + 1) & ~1);              // [K+1][KD][NL]  xhat first rows: group A -> group B
+    double* s_din = s_xf + (K + 1) * KD * NL;                 // [K+1][KL][NL]  din of the tiles between B1 and B2
+    double* s_tin = s_din + (K + 1) * KL * NL;                // [KD][NL]
     uint64_t* fullA = reinterpret_cast<uint64_t*>(s_tin + KD * NL);
     uint64_t* doneA = fullA + DIST_NBUF;
     uint64_t* fullD = doneA + DIST_NBUF;
     uint64_t* doneD = fullD + DIST_NBUF;
     uint64_t* tabbar = doneD + DIST_NBUF;
-    volatile int* stored = reinterpret_cast<volatile int*>(tabbar + 1);  // tiles whose pass-A store is complete
+    uint64_t* xf_full = tabbar + 1;        // [K+1]
+    uint64_t* xf_free = xf_full + (K + 1); // [K+1]
+    volatile int* stored = reinterpret_cast<volatile int*>(xf_free + (K + 1));  // tiles whose pass-A store is complete
 
     pdl_launch();
     if (tid == 0) {
@@ -100,9 +111,23 @@ __global__ void __launch_bounds__(352, 1)
             mbar_init(&fullD[b], 1);
             mbar_init(&doneD[b], 1);
         }
+        for (int b = 0; b <= K; ++b) {
+            mbar_init(&xf_full[b], 1);
+            mbar_init(&xf_free[b], 1);
+        }
         mbar_init(tabbar, 1);
         *stored = 0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // pad rows of both rings (rows past the slab read as zero) and the segment tables of this slab
+    {
+        const int nthr = (int) blockDim.x;
+        const int pad0 = n * NL, pad = tile_doubles - pad0;
+        for (int i = tid; i < 2 * DIST_NBUF * pad; i += nthr) ringA[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
+        const int a = D.row_base;
+        for (int i = tid; i < n * KC; i += nthr) s_cf[i] = T.cf[(size_t) a * KC + i];
+        for (int i = tid; i < KL * KL; i += nthr) s_E[i] = T.E[(size_t) r * KL * KL + i];
+        for (int i = tid; i < KD * KL; i += nthr) s_XiF[i] = T.XiF[(size_t) r * KD * KL + i];
     }
     __syncthreads();
 
@@ -113,9 +138,11 @@ __global__ void __launch_bounds__(352, 1)
         bx = t % G.nb0;
         m = t / G.nb0;
     };
+    const long long L = (long long) G.L0 * G.L1;
 
-    if (tid >= ncons) {
-        if (tid == ncons) {
+    if (tid >= ncons + NB) {
+        const int pt = tid - ncons - NB;
+        if (pt == 0) {
             // ---------------------------------------------------------------- producer of ring A (pass A)
             mbar_expect_tx(tabbar, (uint32_t) (F0.blob_doubles * 8));
             bulk_g2s(s_tab, F0.cfF, (uint32_t) (F0.blob_doubles * 8), tabbar);
@@ -145,14 +172,13 @@ __global__ void __launch_bounds__(352, 1)
                 mbar_wait(&doneA[j % DIST_NBUF], (uint32_t) ((j / DIST_NBUF) & 1));
                 store(j);
                 // all but the two most recent stores have reached memory: tiles 0 .. j-2 may be read back
-                // (pass B trails by 2K >= 2 tiles, so this never holds the ring up)
                 asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
                 if (j >= 1) *stored = j - 1;
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             __threadfence_block();
             *stored = my_count;
-        } else if (tid == ncons + 32) {
+        } else if (pt == 32) {
             // ---------------------------------------------------------------- producer of ring D (pass B)
             pdl_wait();
             auto load = [&](int i) {
@@ -188,18 +214,83 @@ __global__ void __launch_bounds__(352, 1)
         return;
     }
 
-    // ---------------------------------------------------------------------- consumer warps
-    // set-up: pad rows of both rings (rows past the slab read as zero), segment tables of this slab
-    {
-        const int pad0 = n * NL, pad = tile_doubles - pad0;
-        for (int i = tid; i < 2 * DIST_NBUF * pad; i += ncons) ringA[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
-        const int a = D.row_base;
-        for (int i = tid; i < n * KC; i += ncons) s_cf[i] = T.cf[(size_t) a * KC + i];
-        for (int i = tid; i < KL * KL; i += ncons) s_E[i] = T.E[(size_t) r * KL * KL + i];
-        for (int i = tid; i < KD * KL; i += ncons) s_XiF[i] = T.XiF[(size_t) r * KD * KL + i];
-        sweep_sync(ncons);
-        mbar_wait(tabbar, 0);
+    if (tid >= ncons) {
+        // ====================================================================== group B
+        const int t = tid - ncons;
+        const int lp = t % NLt, rg = t / NLt;   // lane pair and first row of this thread in pass B
+        constexpr int RG = NB / NLt;            // rows advance by RG
+        for (int jj = 0; jj < my_count + K; ++jj) {
+            const int j1 = jj, j2 = jj - K;
+            const bool do1 = j1 < my_count, do2 = j2 >= 0;
+            int bx1 = 0, m1 = 0, bx2 = 0, m2 = 0;
+            if (do1) tile_of(j1, bx1, m1);
+            if (do2) tile_of(j2, bx2, m2);
+            const long long line1 = (long long) bx1 * NL + (long long) m1 * G.L0;
+            const long long line2 = (long long) bx2 * NL + (long long) m2 * G.L0;
+            const int lanes1 = min(NL, G.L0 - bx1 * NL), lanes2 = min(NL, G.L0 - bx2 * NL);
+            double* dn1 = s_din + (size_t) (j1 % (K + 1)) * KL * NL;
+            // ---- the boundary values both stages need: the previous rank's Dseg (tile j1), the next rank's X (j2)
+            if (do1)
+                for (int i = t; i < KL * NL; i += NB) {
+                    const int kk = i / NL, ln = i % NL;
+                    dn1[i] = (r > 0 && ln < lanes1)
+                                 ? take_value(D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + line1 + ln, D.error_flag) : 0.0;
+                }
+            if (do2)
+                for (int i = t; i < KD * NL; i += NB) {
+                    const int ii = i / NL, ln = i % NL;
+                    s_tin[i] = (r + 1 < S && ln < lanes2)
+                                   ? take_value(D.x_local + ((size_t) (r + 1) * KD + ii) * L + line2 + ln, D.error_flag) : 0.0;
+                }
+            if (do1) mbar_wait(&xf_full[j1 % (K + 1)], (uint32_t) ((j1 / (K + 1)) & 1));
+            if (do2) mbar_wait(&fullD[j2 % DIST_NBUF], (uint32_t) ((j2 / DIST_NBUF) & 1));
+            group_sync(2, NB);
+            // ---- B1: X = xhat[first KD rows] + XiF din  -> previous rank
+            if (do1 && D.x_prev) {
+                const double* xf = s_xf + (size_t) (j1 % (K + 1)) * KD * NL;
+                for (int i = t; i < KD * NL; i += NB) {
+                    const int ii = i / NL, ln = i % NL;
+                    if (ln < lanes1) {
+                        double acc = xf[i];
+#pragma unroll
+                        for (int q = 0; q < KL; ++q) acc = fma(s_XiF[ii * KL + q], dn1[q * NL + ln], acc);
+                        D.x_prev[((size_t) r * KD + ii) * L + line1 + ln] = acc;
+                    }
+                }
+            }
+            // ---- B2: x = xhat + Psi tin + Xi din on the tile that came back
+            if (do2) {
+                const int b = j2 % DIST_NBUF;
+                double* tile = ringD + (size_t) b * tile_doubles;
+                const double* dn2 = s_din + (size_t) (j2 % (K + 1)) * KL * NL;
+                double2 st[KC];
+#pragma unroll
+                for (int k = 0; k < KD; ++k) st[k] = *reinterpret_cast<const double2*>(s_tin + k * NL + 2 * lp);
+#pragma unroll
+                for (int k = 0; k < KL; ++k) st[KD + k] = *reinterpret_cast<const double2*>(dn2 + k * NL + 2 * lp);
+                for (int row = rg; row < n; row += RG) {
+                    double2 acc = *reinterpret_cast<const double2*>(tile + (size_t) row * NL + 2 * lp);
+                    const double* cf = s_cf + (size_t) row * KC;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) {
+                        acc.x = fma(cf[k], st[k].x, acc.x);
+                        acc.y = fma(cf[k], st[k].y, acc.y);
+                    }
+                    *reinterpret_cast<double2*>(tile + (size_t) row * NL + 2 * lp) = acc;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            group_sync(2, NB);
+            if (t == 0) {
+                if (do1) mbar_arrive(&xf_free[j1 % (K + 1)]);
+                if (do2) mbar_arrive(&doneD[j2 % DIST_NBUF]);
+            }
+        }
+        return;
     }
+
+    // ========================================================================== group A
+    mbar_wait(tabbar, 0);
     SweepFactor F = F0;
     F.cfF = s_tab;
     F.cfB = s_tab + F0.off[0];
@@ -209,123 +300,56 @@ __global__ void __launch_bounds__(352, 1)
     F.W = s_tab + F0.off[4];
     F.V = s_tab + F0.off[5];
     const int tx = tid % NLt;
-    const int craw = tid / NLt;
-    const int c = min(craw, SC - 1);  // padding threads shadow the last chunk in pass A (identical values)
+    const int c = min(tid / NLt, SC - 1);  // padding threads shadow the last chunk (identical values)
     const int j0 = c * CH;
-    const long long L = (long long) G.L0 * G.L1;
-
-    for (int it = 0; it < my_count + 2 * K; ++it) {
-        // ================================================================== A: tile it
-        if (it < my_count) {
-            const int b = it % DIST_NBUF;
-            double* tile = ringA + (size_t) b * tile_doubles;
-            mbar_wait(&fullA[b], (uint32_t) ((it / DIST_NBUF) & 1));
-            double v[RL][CH + KL];
-            {
-                const double* mine = tile + (size_t) j0 * NL + 2 * tx;
+    for (int it = 0; it < my_count; ++it) {
+        const int b = it % DIST_NBUF;
+        double* tile = ringA + (size_t) b * tile_doubles;
+        mbar_wait(&fullA[b], (uint32_t) ((it / DIST_NBUF) & 1));
+        double v[RL][CH + KL];
+        {
+            const double* mine = tile + (size_t) j0 * NL + 2 * tx;
 #pragma unroll
-                for (int q = 0; q < CH + KL; ++q) {
-                    const double2 t2 = *reinterpret_cast<const double2*>(mine + q * NL);
-                    v[0][q] = t2.x;
-                    v[1][q] = t2.y;
-                }
+            for (int q = 0; q < CH + KL; ++q) {
+                const double2 t2 = *reinterpret_cast<const double2*>(mine + q * NL);
+                v[0][q] = t2.x;
+                v[1][q] = t2.y;
             }
-            sweep_core<KL, KD, PIV, CH, RL, true>(F, v, fst, bst, c, tx, NLt, SC, ncons);
-            {
-                double* mine = tile + (size_t) j0 * NL + 2 * tx;
-#pragma unroll
-                for (int q = 0; q < CH; ++q)
-                    if (j0 + q < n) *reinterpret_cast<double2*>(mine + q * NL) = make_double2(v[0][q], v[1][q]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            sweep_sync(ncons);
-            // the tile is final for pass A: keep its first KD rows for B1, send Dseg to the next rank
-            int bx, m;
-            tile_of(it, bx, m);
-            const long long line0 = (long long) bx * NL + (long long) m * G.L0;
-            const int lanes = min(NL, G.L0 - bx * NL);
-            double* xf = s_xf + (size_t) (it % (K + 1)) * KD * NL;
-            for (int i = tid; i < KD * NL; i += ncons) xf[i] = tile[i];  // rows 0 .. KD-1 are the first KD*NL doubles
-            if (D.dseg_next) {
-                for (int i = tid; i < KL * NL; i += ncons) {
-                    const int kk = i / NL, ln = i % NL;
-                    if (ln < lanes) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int mm = 0; mm < KL; ++mm) acc = fma(s_E[kk * KL + mm], tile[(size_t) (n - KL + mm) * NL + ln], acc);
-                        D.dseg_next[((size_t) r * KL + kk) * L + line0 + ln] = acc;
-                    }
-                }
-            }
-            sweep_sync(ncons);
-            if (tid == 0) mbar_arrive(&doneA[b]);
         }
-        // ================================================================== B1: tile it - K
-        const int j1 = it - K;
-        if (j1 >= 0 && j1 < my_count) {
-            int bx, m;
-            tile_of(j1, bx, m);
-            const long long line0 = (long long) bx * NL + (long long) m * G.L0;
-            const int lanes = min(NL, G.L0 - bx * NL);
-            double* dn = s_din + (size_t) (j1 % (2 * K + 1)) * KL * NL;
+        sweep_core<KL, KD, PIV, CH, RL, true>(F, v, fst, bst, c, tx, NLt, SC, ncons);
+        {
+            double* mine = tile + (size_t) j0 * NL + 2 * tx;
+#pragma unroll
+            for (int q = 0; q < CH; ++q)
+                if (j0 + q < n) *reinterpret_cast<double2*>(mine + q * NL) = make_double2(v[0][q], v[1][q]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // slot of the hand-over ring: free once group B has used its previous content
+        const int xs = it % (K + 1), use = it / (K + 1);
+        if (use > 0) mbar_wait(&xf_free[xs], (uint32_t) ((use - 1) & 1));
+        sweep_sync(ncons);
+        // the tile is final for pass A: its first KD rows go to group B, Dseg to the next rank
+        int bx, m;
+        tile_of(it, bx, m);
+        const long long line0 = (long long) bx * NL + (long long) m * G.L0;
+        const int lanes = min(NL, G.L0 - bx * NL);
+        double* xf = s_xf + (size_t) xs * KD * NL;
+        for (int i = tid; i < KD * NL; i += ncons) xf[i] = tile[i];  // rows 0 .. KD-1 are the first KD*NL doubles
+        if (D.dseg_next) {
             for (int i = tid; i < KL * NL; i += ncons) {
                 const int kk = i / NL, ln = i % NL;
-                dn[i] = (r > 0 && ln < lanes) ? take_value(D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + line0 + ln, D.error_flag) : 0.0;
-            }
-            sweep_sync(ncons);
-            if (D.x_prev) {
-                const double* xf = s_xf + (size_t) (j1 % (K + 1)) * KD * NL;
-                for (int i = tid; i < KD * NL; i += ncons) {
-                    const int ii = i / NL, ln = i % NL;
-                    if (ln < lanes) {
-                        double acc = xf[i];
+                if (ln < lanes) {
+                    double acc = 0.0;
 #pragma unroll
-                        for (int q = 0; q < KL; ++q) acc = fma(s_XiF[ii * KL + q], dn[q * NL + ln], acc);
-                        D.x_prev[((size_t) r * KD + ii) * L + line0 + ln] = acc;
-                    }
+                    for (int mm = 0; mm < KL; ++mm) acc = fma(s_E[kk * KL + mm], tile[(size_t) (n - KL + mm) * NL + ln], acc);
+                    D.dseg_next[((size_t) r * KL + kk) * L + line0 + ln] = acc;
                 }
             }
         }
-        // ================================================================== B2: tile it - 2K
-        const int j2 = it - 2 * K;
-        if (j2 >= 0 && j2 < my_count) {
-            int bx, m;
-            tile_of(j2, bx, m);
-            const long long line0 = (long long) bx * NL + (long long) m * G.L0;
-            const int lanes = min(NL, G.L0 - bx * NL);
-            const int b = j2 % DIST_NBUF;
-            double* tile = ringD + (size_t) b * tile_doubles;
-            const double* dn = s_din + (size_t) (j2 % (2 * K + 1)) * KL * NL;
-            for (int i = tid; i < KD * NL; i += ncons) {
-                const int ii = i / NL, ln = i % NL;
-                s_tin[i] = (r + 1 < S && ln < lanes) ? take_value(D.x_local + ((size_t) (r + 1) * KD + ii) * L + line0 + ln, D.error_flag) : 0.0;
-            }
-            mbar_wait(&fullD[b], (uint32_t) ((j2 / DIST_NBUF) & 1));
-            sweep_sync(ncons);
-            if (craw < SC) {
-                double2 st[KC];
-#pragma unroll
-                for (int k = 0; k < KD; ++k) st[k] = *reinterpret_cast<const double2*>(s_tin + k * NL + 2 * tx);
-#pragma unroll
-                for (int k = 0; k < KL; ++k) st[KD + k] = *reinterpret_cast<const double2*>(dn + k * NL + 2 * tx);
-                double* mine = tile + (size_t) j0 * NL + 2 * tx;
-#pragma unroll
-                for (int q = 0; q < CH; ++q) {
-                    if (j0 + q < n) {
-                        double2 acc = *reinterpret_cast<const double2*>(mine + q * NL);
-                        const double* cf = s_cf + (size_t) (j0 + q) * KC;
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) {
-                            acc.x = fma(cf[k], st[k].x, acc.x);
-                            acc.y = fma(cf[k], st[k].y, acc.y);
-                        }
-                        *reinterpret_cast<double2*>(mine + q * NL) = acc;
-                    }
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            sweep_sync(ncons);
-            if (tid == 0) mbar_arrive(&doneD[b]);
+        sweep_sync(ncons);
+        if (tid == 0) {
+            mbar_arrive(&doneA[b]);
+            mbar_arrive(&xf_full[xs]);
         }
     }
 }
@@ -365,7 +389,7 @@ int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G,
     if (NL != 16 && NL != 32 && NL != 64) return -1;
     const int NLt = NL / SWEEP_RL;
     const int ncons = (NLt * F.SC + 31) / 32 * 32;
-    if (ncons > 288 || D.lag < 1 || D.lag > 16) return -1;
+    if (ncons > 192 || NLt > DIST_NB || DIST_NB % NLt != 0 || D.lag < 1 || D.lag > 16) return -1;
     if ((uintptr_t) F.cfF % 16 != 0 || F.blob_doubles % 2 != 0) return -1;
     SweepTileGeom Tg{};
     Tg.in = G.in;
@@ -384,8 +408,8 @@ int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G,
     const int KC = T.KD + T.KL, K = D.lag;
     const size_t doubles = (size_t) 2 * DIST_NBUF * Tg.tile_doubles + (size_t) F.SC * (F.KL + F.KD) * NL + F.blob_doubles +
                            ((F.n * KC + 1) & ~1) + ((T.KL * T.KL + 1) & ~1) + ((T.KD * T.KL + 1) & ~1) +
-                           (size_t) (K + 1) * T.KD * NL + (size_t) (2 * K + 1) * T.KL * NL + (size_t) T.KD * NL;
-    const size_t smem = doubles * 8 + (4 * DIST_NBUF + 1) * 8 + 64;
+                           (size_t) (K + 1) * T.KD * NL + (size_t) (K + 1) * T.KL * NL + (size_t) T.KD * NL;
+    const size_t smem = doubles * 8 + (4 * DIST_NBUF + 1 + 2 * (K + 1)) * 8 + 64;
     if (smem > 226 * 1024) return -1;
     dist_kern_t k = pick(F.KL, F.piv != 0, NL);
     if (!k) return -1;
@@ -399,7 +423,7 @@ int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G,
         return v;
     }();
     int cap = (G.max_ctas > 0 && G.max_ctas < sms) ? G.max_ctas : sms;
-    dim3 block(ncons + 64, 1, 1), grid(Tg.ntiles < cap ? Tg.ntiles : cap, 1, 1);
+    dim3 block(ncons + DIST_NB + 64, 1, 1), grid(Tg.ntiles < cap ? Tg.ntiles : cap, 1, 1);
     return (int) launch_ex(k, grid, block, smem, st, true, F, T, Tg, D);
 }
 

@@ -471,7 +471,7 @@ def test_slab_virtual_ranks_vs_oracle(oracle, problem, world, p, ne, dt):
 
 
 @pytest.mark.parametrize("p,ne_z,world,nx,ny,lag,nl", [(2, 126, 2, 40, 24, 4, 16), (2, 190, 3, 70, 10, 2, 32),
-                                                      (3, 250, 2, 36, 20, 1, 32), (4, 388, 2, 34, 6, 3, 16),
+                                                      (3, 250, 2, 36, 20, 1, 32), (4, 196, 2, 34, 6, 3, 16),
                                                       (2, 510, 8, 130, 9, 4, 64)])
 def test_fused_dist_sweep_equals_dgbtrs(oracle, p, ne_z, world, nx, ny, lag, nl):
     """the ONE-kernel distributed z sweep (pass A + neighbour exchange through flags + pass B,
@@ -549,3 +549,21 @@ def test_slab_cluster_fused_and_unfused_vs_oracle(oracle, monkeypatch, fused):
     cl.step(2)
     want, _ = oracle.run("heat_3d", p, ne, dt, 2, u0=u0)
     assert rel_l2(cl.state(), want) < 2 * TOL_STEP
+
+
+# ---------------------------------------------------------------------- set-up on the device (projection)
+def test_device_projection_and_shipped_runs_vs_reference_golden(golden):
+    """before() of every example on the device -- compute_projection of the shipped initial state
+    (include/ads/projection.hpp:60-107 through adsb_project_init / adsb_load_tensor) followed by ads_solve --
+    and then the whole shipped run, against the compiled reference's own output for the same run."""
+    g = golden["problems"]
+    for tag in _problem_tags(g):
+        pid, p, ne, ns = (int(v) for v in g[tag + "_meta"])
+        dt = float(g[tag + "_dt"][0])
+        sim = ads.PROBLEMS[NAMES[pid]](p, ne, ads.timesteps_config(ns, dt))
+        sim.before()
+        tol = step_tol(g, tag)
+        assert rel_l2(sim.state(), g[tag + "_shipped_init"]) < tol, (tag, "initial state")
+        if ns <= 5:
+            sim.advance(ns)
+            assert rel_l2(sim.state(), g[tag + "_shipped"]) < (ns + 1) * tol, (tag, "shipped run")
