@@ -23,6 +23,7 @@ struct SegSet {  // adsb_set_axis_segments: tables + the pass-A factor of every 
     std::vector<int> bounds;
     int local_lo = 0, local_cnt = 0;
     std::vector<SweepFactor> local;  // [local_cnt]
+    std::vector<SweepFactor> local_dist;  // the same factors with chunks of SWEEP_CH_DIST columns (fused kernel), or empty
     std::vector<void*> allocs;
 };
 
@@ -35,6 +36,7 @@ struct DevFactor {
     std::vector<double> ab;
     std::vector<int> ipiv;
     SegSet seg;
+    bool auto_seg = false;  // segments were cut by the library because the line is too long for one CTA
 };
 
 struct AxisData {
@@ -75,6 +77,12 @@ struct adsb_ctx {
     long long launches = 0;
     int sm_limit = 0;  // adsb_set_sm_limit
     RhsSide side;      // second stream + events for the x-remainder kernel of the right-hand side (lazy)
+    // lines too long for one CTA (> 576 rows) are swept in segments (kernels_seg.cu): pass A of the segments
+    // runs on a few streams side by side; boundary-state scratch is shared by all axes
+    std::vector<cudaStream_t> seg_streams;
+    std::vector<cudaEvent_t> seg_events;  // [0] fork, [1 + i] join of stream i
+    double* seg_scratch = nullptr;
+    size_t seg_scratch_doubles = 0;
     // Managed tensors keep the reference's index order (x fastest) but pad every x row to an EVEN number of
     // doubles: rows, planes and the tensor itself then start 16 B aligned, which is what the TMA-fed
     // kernels need (n = elements + p is odd for every odd degree).  The pad column is never read as data.
@@ -151,6 +159,86 @@ int ensure_buf(adsb_ctx* c, int b) {
     return ADSB_OK;
 }
 
+
+// segment tables + pass-A factors of the local segments for an uploaded factor
+int set_segments_impl(adsb_ctx* c, DevFactor& D, int nseg, const int* bounds, int local_lo, int local_cnt) {
+    SegPlan P;
+    // chain cut-off 1e-17: dropped products change the result by less than a tenth of the unit round-off
+    if (int rc = build_segment_plan(D.n, D.kl, D.ku, D.ldab, D.ab.data(), D.ipiv.data(), nseg, bounds, 1e-17, P)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    free_segments(D.seg);
+    SegSet& g = D.seg;
+    int* d_bounds;
+    double *E, *Wf, *Vb, *XiF, *cf;
+    if (int rc = upload_vec(P.bounds, 0, &d_bounds, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.E, 0, &E, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.Wf, 0, &Wf, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.Vb, 0, &Vb, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.XiF, 0, &XiF, &g.allocs)) return rc;
+    if (int rc = upload_vec(P.cf, 0, &cf, &g.allocs)) return rc;
+    g.dev = SegDev{P.n, P.KL, P.KD, P.S, P.DF, P.DB, d_bounds, E, Wf, Vb, XiF, cf};
+    g.bounds = P.bounds;
+    g.local_lo = local_lo;
+    g.local_cnt = local_cnt;
+    g.local.resize(local_cnt);
+    for (int i = 0; i < local_cnt; ++i) {
+        // pass-A factor of segment s: the factor's own columns [a, b), pivots renumbered
+        const int a = P.bounds[local_lo + i], b = P.bounds[local_lo + i + 1];
+        std::vector<int> ip(D.ipiv.begin() + a, D.ipiv.begin() + b);
+        for (int& v : ip) v -= a;
+        SweepPlan L;
+        if (int rc = build_sweep_plan(b - a, D.kl, D.ku, D.ldab, D.ab.data() + (size_t) a * D.ldab, ip.data(), SWEEP_CH, 1, L,
+                                      P.piv != 0))
+            return rc;
+        if (int rc = upload_plan(L, g.local[i], g.allocs)) return rc;
+        // the fused distributed sweep prefers shorter chunks (more threads per tile); only slabs use it
+        if (local_cnt == 1 && L.KD <= SWEEP_CH_DIST) {
+            SweepPlan Ld;
+            if (build_sweep_plan(b - a, D.kl, D.ku, D.ldab, D.ab.data() + (size_t) a * D.ldab, ip.data(), SWEEP_CH_DIST, 1, Ld,
+                                 P.piv != 0) == ADSB_OK && Ld.KL == L.KL && Ld.KD == L.KD) {
+                g.local_dist.resize(1);
+                if (int rc = upload_plan(Ld, g.local_dist[0], g.allocs)) return rc;
+            }
+        }
+    }
+    g.set = true;
+    return ADSB_OK;
+}
+
+int device_sms() {
+    static int sms = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return sms;
+}
+
+// Lines too long for one CTA of the tile kernel: segments of <= 520 rows (29 chunks), cut where no row
+// interchange crosses.  Silently leaves the factor unsegmented when that is impossible (growing boundary
+// responses ...): the register-path kernel then handles the line as before.
+void try_auto_segments(adsb_ctx* c, DevFactor& D) {
+    D.auto_seg = false;
+    static const bool on = [] {
+        const char* e = getenv("ADSB_AUTO_SEGMENTS");
+        return !e || atoi(e) != 0;
+    }();
+    if (!on || D.f.SC <= 32) return;
+    const int S = (D.n + 519) / 520;
+    std::vector<int> bounds(S + 1);
+    const std::string keep = g_last_error;
+    if (pick_segment_bounds(D.n, D.kl, D.ipiv.data(), S, 2, std::max(D.kl + D.ku, 2), bounds.data()) == ADSB_OK) {
+        bool even = true;
+        for (int s = 1; s < S; ++s) even = even && (bounds[s] % 2 == 0);
+        if (even && set_segments_impl(c, D, S, bounds.data(), 0, S) == ADSB_OK) D.auto_seg = true;
+    }
+    if (!D.auto_seg) {
+        free_segments(D.seg);
+        g_last_error = keep;
+    }
+}
+
 cudaEvent_t get_event(adsb_ctx* c) {
     if (!c->free_events.empty()) {
         cudaEvent_t e = c->free_events.back();
@@ -212,6 +300,19 @@ int get_offsets(adsb_ctx* c, const long long* host, int n, const long long** dev
     return ADSB_OK;
 }
 
+int sweep_segmented(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view& vi, double* out,
+                    const adsb_view& vo, bool managed);
+
+// Lines that follow one another in memory (unit stride along l0, l1 stride = L0: the z lines of an x-fastest
+// tensor without row padding): number them flat, so tiles of NL lines never end half empty at a row end.
+void flatten_lines(SweepGeom& G) {
+    if (G.L1 > 1 && G.s0_in == 1 && G.s0_out == 1 && G.s1_in == G.L0 && G.s1_out == G.L0 &&
+        (long long) G.L0 * G.L1 < (1ll << 30)) {
+        G.L0 *= G.L1;
+        G.L1 = 1;
+    }
+}
+
 // sweep along `axis` of a view; see adsb_sweep_view
 int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view& vi,
                const long long* off_in_h, double* out, const adsb_view& vo, const long long* off_out_h,
@@ -220,6 +321,8 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     if (slot < 0 || slot >= ADSB_MAX_SLOTS || !c->ax[axis].fac[slot].set)
         return fail(ADSB_ESTATE, "sweep: no factor uploaded for this axis/slot");
     const SweepFactor& F = Fsel ? *Fsel : c->ax[axis].fac[slot].f;
+    if (!Fsel && c->ax[axis].fac[slot].auto_seg && !off_in_h && !off_out_h && vi.n[axis] == F.n)
+        return sweep_segmented(c, axis, slot, in, vi, out, vo, managed);
     for (int d = 0; d < 3; ++d)
         if (vi.n[d] != vo.n[d]) return fail(ADSB_EINVAL, "sweep: in/out extents differ");
     if (vi.n[axis] != F.n) return fail(ADSB_EINVAL, "sweep: the view does not span the whole axis");
@@ -253,6 +356,7 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     G.s1_in = vi.s[l1];
     G.s1_out = vo.s[l1];
     G.max_ctas = c->sm_limit;
+    if (!contig && !off_in && !off_out) flatten_lines(G);
     // managed tensors pad every x row: an in-place x sweep of an odd-length line may move the pad along
     G.pad_ok = managed && in == out && axis == 0 && vi.s[1] > vi.n[0];
     G.pitch = F.n + (F.n & 1);
@@ -492,6 +596,9 @@ int adsb_destroy(adsb_ctx* c) {
         cudaEventDestroy(s.b);
     }
     for (auto e : c->free_events) cudaEventDestroy(e);
+    for (auto st : c->seg_streams) cudaStreamDestroy(st);
+    for (auto e : c->seg_events) cudaEventDestroy(e);
+    cudaFree(c->seg_scratch);
     if (c->side.side) {
         cudaStreamDestroy(c->side.side);
         cudaEventDestroy(c->side.fork);
@@ -608,6 +715,8 @@ int adsb_set_axis_factor(adsb_ctx* c, int axis, int slot, int n, int kl, int ku,
     D.ldab = ldab;
     D.ab.assign(ab, ab + (size_t) ldab * n);
     D.ipiv.assign(ipiv, ipiv + n);
+    D.set = true;
+    try_auto_segments(c, D);
     D.set = true;
     return ADSB_OK;
 }
@@ -945,6 +1054,89 @@ int seg_check_rows(const SegSet& g, int s_lo, int s_hi, int row_base, int rows) 
 
 }  // namespace
 
+namespace {
+
+// All segments of every line on this GPU (lines longer than one CTA can hold): pass A of the segments side by
+// side on a few streams (each a persistent kernel on its share of the SMs), then the boundary kernels and pass B.
+int sweep_segmented(adsb_ctx* c, int axis, int slot, const double* in, const adsb_view& vi, double* out,
+                    const adsb_view& vo, bool managed) {
+    DevFactor& D = c->ax[axis].fac[slot];
+    SegSet& g = D.seg;
+    const int S = g.dev.S, KL = g.dev.KL, KD = g.dev.KD;
+    SegGeom G;
+    if (int rc = seg_geom(c, axis, out, vo, out, vo, 0, 0, S, G)) return rc;
+    const size_t L = (size_t) G.L0 * G.L1;
+    const size_t need = (size_t) S * (2 * KL + 2 * KD) * L;
+    if (c->seg_scratch_doubles < need) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->seg_scratch);
+        c->seg_scratch = nullptr;
+        c->seg_scratch_doubles = 0;
+        CU(cudaMalloc((void**) &c->seg_scratch, need * sizeof(double)));
+        c->seg_scratch_doubles = need;
+    }
+    double* dseg = c->seg_scratch;
+    double* xst = dseg + (size_t) S * KL * L;
+    double* din = xst + (size_t) S * KD * L;
+    double* tin = din + (size_t) S * KL * L;
+    const int ns = std::min(S, 8);
+    while ((int) c->seg_streams.size() < ns) {
+        cudaStream_t st;
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        c->seg_streams.push_back(st);
+    }
+    while ((int) c->seg_events.size() < ns + 1) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->seg_events.push_back(e);
+    }
+    StageTimer t(c, 1 + axis);
+    cudaStream_t main_stream = c->stream;
+    const int keep_limit = c->sm_limit;
+    const bool keep_timing = c->timing;
+    const int sms = (keep_limit > 0 && keep_limit < device_sms()) ? keep_limit : device_sms();
+    CU(cudaEventRecord(c->seg_events[0], main_stream));
+    int rc = ADSB_OK;
+    c->timing = false;
+    c->sm_limit = std::max(1, sms / ns);
+    for (int s = 0; s < S && rc == ADSB_OK; ++s) {
+        cudaStream_t st = c->seg_streams[s % ns];
+        if (s < ns) CU(cudaStreamWaitEvent(st, c->seg_events[0], 0));
+        const int a = g.bounds[s], rows = g.bounds[s + 1] - a;
+        adsb_view svi = vi, svo = vo;
+        svi.n[axis] = svo.n[axis] = rows;
+        c->stream = st;
+        rc = sweep_impl(c, axis, slot, in + (long long) a * vi.s[axis], svi, nullptr, out + (long long) a * vo.s[axis], svo,
+                        nullptr, managed, &g.local[s]);
+    }
+    c->stream = main_stream;
+    c->sm_limit = keep_limit;
+    c->timing = keep_timing;
+    if (rc != ADSB_OK) return rc;
+    for (int i = 0; i < ns; ++i) {
+        CU(cudaEventRecord(c->seg_events[1 + i], c->seg_streams[i]));
+        CU(cudaStreamWaitEvent(main_stream, c->seg_events[1 + i], 0));
+    }
+    double* dst1[1] = {dseg};
+    double* dst2[1] = {xst};
+    cudaError_t e = (cudaError_t) launch_seg_dseg(g.dev, G, dst1, 1, main_stream);
+    if (e == cudaSuccess) e = (cudaError_t) launch_seg_din(g.dev, G, dseg, din, dst2, 1, main_stream);
+    const double* back = xst;
+    if (e == cudaSuccess && g.dev.DB > 1) {
+        e = (cudaError_t) launch_seg_tin(g.dev, 0, S, (long long) L, xst, tin, main_stream);
+        back = tin;
+        c->launches++;
+    }
+    int max_rows = 0;
+    for (int s = 0; s < S; ++s) max_rows = std::max(max_rows, g.bounds[s + 1] - g.bounds[s]);
+    if (e == cudaSuccess) e = (cudaError_t) launch_seg_correct(g.dev, G, din, back, g.dev.DB == 1 ? 1 : 0, max_rows, main_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "segmented sweep kernels");
+    c->launches += 3;
+    return ADSB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int adsb_set_axis_segments(adsb_ctx* c, int axis, int slot, int nseg, const int* bounds, int local_lo, int local_cnt) {
@@ -954,39 +1146,8 @@ int adsb_set_axis_segments(adsb_ctx* c, int axis, int slot, int nseg, const int*
     if (!bounds || nseg < 1 || local_lo < 0 || local_cnt < 0 || local_lo + local_cnt > nseg)
         return fail(ADSB_EINVAL, "set_axis_segments: bad segment arguments");
     if (int rc = select_device(c)) return rc;
-    DevFactor& D = c->ax[axis].fac[slot];
-    SegPlan P;
-    // chain cut-off 1e-17: dropped products change the result by less than a tenth of the unit round-off
-    if (int rc = build_segment_plan(D.n, D.kl, D.ku, D.ldab, D.ab.data(), D.ipiv.data(), nseg, bounds, 1e-17, P)) return rc;
-    CU(cudaStreamSynchronize(c->stream));
-    free_segments(D.seg);
-    SegSet& g = D.seg;
-    int* d_bounds;
-    double *E, *Wf, *Vb, *XiF, *cf;
-    if (int rc = upload_vec(P.bounds, 0, &d_bounds, &g.allocs)) return rc;
-    if (int rc = upload_vec(P.E, 0, &E, &g.allocs)) return rc;
-    if (int rc = upload_vec(P.Wf, 0, &Wf, &g.allocs)) return rc;
-    if (int rc = upload_vec(P.Vb, 0, &Vb, &g.allocs)) return rc;
-    if (int rc = upload_vec(P.XiF, 0, &XiF, &g.allocs)) return rc;
-    if (int rc = upload_vec(P.cf, 0, &cf, &g.allocs)) return rc;
-    g.dev = SegDev{P.n, P.KL, P.KD, P.S, P.DF, P.DB, d_bounds, E, Wf, Vb, XiF, cf};
-    g.bounds = P.bounds;
-    g.local_lo = local_lo;
-    g.local_cnt = local_cnt;
-    g.local.resize(local_cnt);
-    for (int i = 0; i < local_cnt; ++i) {
-        // pass-A factor of segment s: the factor's own columns [a, b), pivots renumbered
-        const int a = P.bounds[local_lo + i], b = P.bounds[local_lo + i + 1];
-        std::vector<int> ip(D.ipiv.begin() + a, D.ipiv.begin() + b);
-        for (int& v : ip) v -= a;
-        SweepPlan L;
-        if (int rc = build_sweep_plan(b - a, D.kl, D.ku, D.ldab, D.ab.data() + (size_t) a * D.ldab, ip.data(), SWEEP_CH, 1, L,
-                                      P.piv != 0))
-            return rc;
-        if (int rc = upload_plan(L, g.local[i], g.allocs)) return rc;
-    }
-    g.set = true;
-    return ADSB_OK;
+    c->ax[axis].fac[slot].auto_seg = false;
+    return set_segments_impl(c, c->ax[axis].fac[slot], nseg, bounds, local_lo, local_cnt);
 }
 
 int adsb_segment_info(adsb_ctx* c, int axis, int slot, int* info8) {
@@ -1009,6 +1170,14 @@ int adsb_seg_sweep_view(adsb_ctx* c, int axis, int slot, int seg, const double* 
     return sweep_impl(c, axis, slot, in, *vin, nullptr, out, *vout, nullptr, false, &g->local[seg - g->local_lo]);
 }
 
+static bool dist_short_chunks() {  // ADSB_DIST_SHORT_CHUNKS=0: keep 18-column chunks in the fused sweep
+    static const bool on = [] {
+        const char* e = getenv("ADSB_DIST_SHORT_CHUNKS");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
 int adsb_dist_sweep_check(adsb_ctx* c, int axis, int slot, int rank, const adsb_view* v, int nl, int lag) {
     SegSet* g;
     if (int rc = seg_of(c, axis, slot, &g)) return rc;
@@ -1024,9 +1193,13 @@ int adsb_dist_sweep_check(adsb_ctx* c, int axis, int slot, int rank, const adsb_
     G.s0_in = G.s0_out = v->s[l0];
     G.s1_in = G.s1_out = v->s[l1];
     if (G.s0_in != 1 || (G.sj_in & 1) || (G.s1_in & 1)) return 0;
+    flatten_lines(G);
     SweepDistArgs D{};
     D.lag = lag > 0 ? lag : 4;
-    return launch_sweep_dist(F, g->dev, G, D, nl, nullptr, true) == 0 ? 1 : 0;
+    if (dist_short_chunks() && !g->local_dist.empty() &&
+        launch_sweep_dist(g->local_dist[0], SWEEP_CH_DIST, g->dev, G, D, nl, nullptr, true) == 0)
+        return 1;
+    return launch_sweep_dist(F, SWEEP_CH, g->dev, G, D, nl, nullptr, true) == 0 ? 1 : 0;
 }
 
 int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const adsb_view* v, const adsb_dist_args* d) {
@@ -1055,6 +1228,7 @@ int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const ad
     G.s0_in = G.s0_out = v->s[l0];
     G.s1_in = G.s1_out = v->s[l1];
     G.max_ctas = c->sm_limit;
+    flatten_lines(G);
     SweepDistArgs D{};
     D.rank = d->rank;
     D.row_base = g->bounds[d->rank];
@@ -1065,7 +1239,10 @@ int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const ad
     D.x_prev = d->rank > 0 ? d->x_prev : nullptr;
     D.error_flag = d->error_flag;
     StageTimer t(c, 1 + axis);
-    const int rc = launch_sweep_dist(F, g->dev, G, D, d->nl, c->stream);
+    int rc = -1;
+    if (dist_short_chunks() && !g->local_dist.empty())
+        rc = launch_sweep_dist(g->local_dist[0], SWEEP_CH_DIST, g->dev, G, D, d->nl, c->stream);
+    if (rc == -1) rc = launch_sweep_dist(F, SWEEP_CH, g->dev, G, D, d->nl, c->stream);
     if (rc == -1) return fail(ADSB_ESTATE, "dist_sweep_view: this factor / view is not eligible for the fused kernel");
     if (rc != 0) return cuda_fail((cudaError_t) rc, "distributed sweep kernel launch");
     c->launches++;

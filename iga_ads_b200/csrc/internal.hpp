@@ -8,6 +8,7 @@
 namespace adsb {
 
 int fail(int code, const std::string& msg);
+extern thread_local std::string g_last_error;  // what adsb_last_error() returns
 
 int gauss_rule(int q, double* x, double* w);
 int make_knots(int p, int elements, double a, double b, double* knot);

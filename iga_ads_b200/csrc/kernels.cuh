@@ -35,6 +35,7 @@ inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 }
 
 constexpr int SWEEP_CH = 18;  // columns per chunk (one chunk per thread, held in registers)
+constexpr int SWEEP_CH_DIST = 12;  // shorter chunks for the fused distributed sweep (kernels_sweep_dist.cu)
 constexpr int SWEEP_RL = 2;   // lines per thread: they share every coefficient load and interleave for ILP
 constexpr int SWEEP_MAX_DEPTH_DEV = 6;
 // Coefficient records (multipliers, U rows, Psi|Xi) of one column: `sweep_rec` doubles are loaded (even: 128-bit
@@ -216,7 +217,7 @@ struct SweepDistArgs {
     int* error_flag;
 };
 // dry_run: only report eligibility (0 / -1), launch nothing
-int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
+int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
                       cudaStream_t st, bool dry_run = false);
 
 // vnx > 0: `values` are the first elements of a tensor with x rows of vnx doubles, vpitch apart (else dense)

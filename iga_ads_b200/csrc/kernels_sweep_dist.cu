@@ -40,26 +40,29 @@ namespace {
 
 constexpr int DIST_NBUF = 2;  // slots per tile ring
 
-// Take one boundary value out of the inbox: spin until the neighbour's store has replaced the sentinel, put the
-// sentinel back.  Gives up after ~2 s (sets *err; the result is then garbage but nothing hangs).
-__device__ __forceinline__ double take_value(double* slot, int* err) {
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(slot);
+// Boundary values validate themselves: a word of the inbox holds the sentinel until the neighbour's store has
+// replaced it.  peek() reads it (possibly still the sentinel), take() spins until the value is there and puts the
+// sentinel back; it gives up after ~2 s (sets *err; the result is then garbage but nothing hangs).
+__device__ __forceinline__ unsigned long long peek_value(const double* slot) {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+    return v;
+}
+__device__ __forceinline__ double take_value(double* slot, unsigned long long v, int* err) {
     if (v == ADSB_DIST_SENTINEL_BITS) {
         const long long t0 = clock64();
         unsigned ns = 32;
         do {
             __nanosleep(ns);
             if (ns < 512) ns *= 2;
-            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            v = peek_value(slot);
             if (clock64() - t0 > 4000000000ll) {
                 if (err) atomicExch(err, 1);
                 break;
             }
         } while (v == ADSB_DIST_SENTINEL_BITS);
     }
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w), "l"(ADSB_DIST_SENTINEL_BITS) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot), "l"(ADSB_DIST_SENTINEL_BITS) : "memory");
     return __longlong_as_double((long long) v);
 }
 
@@ -219,29 +222,68 @@ __global__ void __launch_bounds__(384, 1)
         const int t = tid - ncons;
         const int lp = t % NLt, rg = t / NLt;   // lane pair and first row of this thread in pass B
         constexpr int RG = NB / NLt;            // rows advance by RG
+        constexpr int NV1 = (KL * NL + NB - 1) / NB, NV2 = (KD * NL + NB - 1) / NB;  // polled words per thread
+        // the words this thread polls for tile j: Dseg of the previous rank (stage B1), X of the next rank (B2)
+        auto slot1 = [&](int j, int v) -> double* {
+            const int i = t + v * NB;
+            if (r == 0 || j < 0 || j >= my_count || i >= KL * NL) return nullptr;
+            int bx, m;
+            tile_of(j, bx, m);
+            const int kk = i / NL, ln = i % NL;
+            if (ln >= min(NL, G.L0 - bx * NL)) return nullptr;
+            return D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + (long long) bx * NL + (long long) m * G.L0 + ln;
+        };
+        auto slot2 = [&](int j, int v) -> double* {
+            const int i = t + v * NB;
+            if (r + 1 >= S || j < 0 || j >= my_count || i >= KD * NL) return nullptr;
+            int bx, m;
+            tile_of(j, bx, m);
+            const int ii = i / NL, ln = i % NL;
+            if (ln >= min(NL, G.L0 - bx * NL)) return nullptr;
+            return D.x_local + ((size_t) (r + 1) * KD + ii) * L + (long long) bx * NL + (long long) m * G.L0 + ln;
+        };
+        // the loads of iteration jj + 1 are issued during iteration jj, so their latency (and, mostly, the wait
+        // for the neighbour) is off the critical path
+        unsigned long long pre1[NV1], pre2[NV2];
+#pragma unroll
+        for (int v = 0; v < NV1; ++v) {
+            double* a = slot1(0, v);
+            pre1[v] = a ? peek_value(a) : 0ull;
+        }
+#pragma unroll
+        for (int v = 0; v < NV2; ++v) {
+            double* a = slot2(-K, v);
+            pre2[v] = a ? peek_value(a) : 0ull;
+        }
         for (int jj = 0; jj < my_count + K; ++jj) {
             const int j1 = jj, j2 = jj - K;
             const bool do1 = j1 < my_count, do2 = j2 >= 0;
-            int bx1 = 0, m1 = 0, bx2 = 0, m2 = 0;
+            int bx1 = 0, m1 = 0;
             if (do1) tile_of(j1, bx1, m1);
-            if (do2) tile_of(j2, bx2, m2);
             const long long line1 = (long long) bx1 * NL + (long long) m1 * G.L0;
-            const long long line2 = (long long) bx2 * NL + (long long) m2 * G.L0;
-            const int lanes1 = min(NL, G.L0 - bx1 * NL), lanes2 = min(NL, G.L0 - bx2 * NL);
+            const int lanes1 = min(NL, G.L0 - bx1 * NL);
             double* dn1 = s_din + (size_t) (j1 % (K + 1)) * KL * NL;
-            // ---- the boundary values both stages need: the previous rank's Dseg (tile j1), the next rank's X (j2)
-            if (do1)
-                for (int i = t; i < KL * NL; i += NB) {
-                    const int kk = i / NL, ln = i % NL;
-                    dn1[i] = (r > 0 && ln < lanes1)
-                                 ? take_value(D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + line1 + ln, D.error_flag) : 0.0;
+            // ---- the boundary values both stages need (zero where there is no neighbour / no line)
+#pragma unroll
+            for (int v = 0; v < NV1; ++v) {
+                const int i = t + v * NB;
+                if (do1 && i < KL * NL) {
+                    double* a = slot1(j1, v);
+                    dn1[i] = a ? take_value(a, pre1[v], D.error_flag) : 0.0;
                 }
-            if (do2)
-                for (int i = t; i < KD * NL; i += NB) {
-                    const int ii = i / NL, ln = i % NL;
-                    s_tin[i] = (r + 1 < S && ln < lanes2)
-                                   ? take_value(D.x_local + ((size_t) (r + 1) * KD + ii) * L + line2 + ln, D.error_flag) : 0.0;
+                double* nx = slot1(j1 + 1, v);
+                pre1[v] = nx ? peek_value(nx) : 0ull;
+            }
+#pragma unroll
+            for (int v = 0; v < NV2; ++v) {
+                const int i = t + v * NB;
+                if (do2 && i < KD * NL) {
+                    double* a = slot2(j2, v);
+                    s_tin[i] = a ? take_value(a, pre2[v], D.error_flag) : 0.0;
                 }
+                double* nx = slot2(j2 + 1, v);
+                pre2[v] = nx ? peek_value(nx) : 0ull;
+            }
             if (do1) mbar_wait(&xf_full[j1 % (K + 1)], (uint32_t) ((j1 / (K + 1)) & 1));
             if (do2) mbar_wait(&fullD[j2 % DIST_NBUF], (uint32_t) ((j2 / DIST_NBUF) & 1));
             group_sync(2, NB);
@@ -356,32 +398,40 @@ __global__ void __launch_bounds__(384, 1)
 
 using dist_kern_t = void (*)(const SweepFactor, const SegDev, const SweepTileGeom, const SweepDistArgs);
 
-template <int P, bool PIV>
+template <int P, bool PIV, int CH>
 dist_kern_t pick_nl(int NL) {
     constexpr int KD = PIV ? 2 * P : P;
-    switch (NL) {
-    case 16: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, SWEEP_CH, 16>;
-    case 32: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, SWEEP_CH, 32>;
-    case 64: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, SWEEP_CH, 64>;
+    if constexpr (KD > CH) return nullptr;
+    else switch (NL) {
+        case 16: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, CH, 16>;
+        case 32: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, CH, 32>;
+        case 64: return (dist_kern_t) sweep_dist_kernel<P, KD, PIV, CH, 64>;
+        default: return nullptr;
+        }
+}
+
+template <int CH>
+dist_kern_t pick_ch(int KL, bool piv, int NL) {
+    switch (KL) {
+    case 1: return piv ? pick_nl<1, true, CH>(NL) : pick_nl<1, false, CH>(NL);
+    case 2: return piv ? pick_nl<2, true, CH>(NL) : pick_nl<2, false, CH>(NL);
+    case 3: return piv ? pick_nl<3, true, CH>(NL) : pick_nl<3, false, CH>(NL);
+    case 4: return piv ? pick_nl<4, true, CH>(NL) : pick_nl<4, false, CH>(NL);
+    case 5: return piv ? pick_nl<5, true, CH>(NL) : pick_nl<5, false, CH>(NL);
     default: return nullptr;
     }
 }
 
-dist_kern_t pick(int KL, bool piv, int NL) {
-    switch (KL) {
-    case 1: return piv ? pick_nl<1, true>(NL) : pick_nl<1, false>(NL);
-    case 2: return piv ? pick_nl<2, true>(NL) : pick_nl<2, false>(NL);
-    case 3: return piv ? pick_nl<3, true>(NL) : pick_nl<3, false>(NL);
-    case 4: return piv ? pick_nl<4, true>(NL) : pick_nl<4, false>(NL);
-    case 5: return piv ? pick_nl<5, true>(NL) : pick_nl<5, false>(NL);
-    default: return nullptr;
-    }
+// chunk length of the slab's factor plan: 18 columns as everywhere, or 12 -- shorter chunks mean more chunks per
+// line, i.e. more threads in the pass-A group of a CTA whose tiles are only 16 .. 64 lines wide
+dist_kern_t pick(int KL, bool piv, int NL, int CH) {
+    return CH == SWEEP_CH ? pick_ch<SWEEP_CH>(KL, piv, NL) : CH == SWEEP_CH_DIST ? pick_ch<SWEEP_CH_DIST>(KL, piv, NL) : nullptr;
 }
 
 }  // namespace
 
 // 0: launched; -1: not eligible (the caller runs pass A / boundary kernels / pass B separately); else cudaError_t
-int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
+int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
                       cudaStream_t st, bool dry_run) {
     if (T.DF != 1 || T.DB != 1) return -1;                   // neighbours only
     if (T.KL != F.KL || T.KD != F.KD) return -1;             // the slab's own factor needs the same kernel variant
@@ -402,7 +452,7 @@ int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G,
     Tg.ntiles = Tg.nb0 * G.L1;
     if (!dry_run)
         if (int rc = sweep_strided_maps(G, F.n, NL, nullptr, nullptr, st, Tg)) return rc;
-    const int rows_needed = F.SC * SWEEP_CH + F.KL;
+    const int rows_needed = F.SC * CH + F.KL;
     Tg.tile_doubles = (rows_needed * NL + 15) & ~15;
     Tg.nbuf = DIST_NBUF;
     const int KC = T.KD + T.KL, K = D.lag;
@@ -411,7 +461,7 @@ int launch_sweep_dist(const SweepFactor& F, const SegDev& T, const SweepGeom& G,
                            (size_t) (K + 1) * T.KD * NL + (size_t) (K + 1) * T.KL * NL + (size_t) T.KD * NL;
     const size_t smem = doubles * 8 + (4 * DIST_NBUF + 1 + 2 * (K + 1)) * 8 + 64;
     if (smem > 226 * 1024) return -1;
-    dist_kern_t k = pick(F.KL, F.piv != 0, NL);
+    dist_kern_t k = pick(F.KL, F.piv != 0, NL, CH);
     if (!k) return -1;
     if (dry_run) return 0;
     cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

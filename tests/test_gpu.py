@@ -87,7 +87,10 @@ def test_ads_solve_mixed_shapes_vs_golden(golden):
 
 
 @pytest.mark.parametrize("p,ne,nd,kind,h,fix", [(2, 62, 3, 0, 0.0, 0), (5, 43, 3, 0, 0.0, 1), (3, 253, 2, 3, 0.005, 0),
-                                               (4, 60, 3, 3, 3.0, 1), (2, 510, 2, 0, 0.0, 0), (3, 29, 3, 0, 0.0, 0)])
+                                               (4, 60, 3, 3, 3.0, 1), (2, 510, 2, 0, 0.0, 0), (3, 29, 3, 0, 0.0, 0),
+                                               # lines longer than one CTA can hold (> 576 rows): cut into segments by
+                                               # the library (pass A per segment, boundary kernels, pass B)
+                                               (3, 1200, 2, 0, 0.0, 1), (2, 1534, 2, 0, 0.0, 0), (5, 700, 2, 0, 0.0, 0)])
 def test_ads_solve_vs_oracle_random(oracle, p, ne, nd, kind, h, fix):
     """ragged sizes (n not a multiple of the chunk length / tile width), pivoting factors"""
     n = ne + p
@@ -101,9 +104,11 @@ def test_ads_solve_vs_oracle_random(oracle, p, ne, nd, kind, h, fix):
     assert rel_l2(ctx.download(U), want) < 1e-13
 
 
-def test_single_axis_sweeps_match_oracle_dgbtrs(oracle):
-    """each axis alone == dgbtrs on the lines of that axis (rotation folded into the kernel)"""
-    p, shape = 2, (37, 21, 18)
+@pytest.mark.parametrize("shape", [(37, 21, 18), (700, 6, 10), (12, 1100, 8), (10, 6, 1300)])
+def test_single_axis_sweeps_match_oracle_dgbtrs(oracle, shape):
+    """each axis alone == dgbtrs on the lines of that axis (rotation folded into the kernel); the long axes are
+    swept in segments"""
+    p = 2
     nes = [s - p for s in shape]
     mats = [ads.matrix_1d(0, p, ne) for ne in nes]
     ctx = make_ctx(shape, mats, [p] * 3, [p] * 3)
@@ -115,7 +120,7 @@ def test_single_axis_sweeps_match_oracle_dgbtrs(oracle):
         want = np.moveaxis(want, -1, 2 - ax)
         ctx.upload(U, rhs)
         ctx.sweep(U, ax)
-        assert rel_l2(ctx.download(U), want) < 1e-14, ax
+        assert rel_l2(ctx.download(U), want) < (1e-14 if max(shape) <= 576 else 5e-14), ax
 
 
 # ---------------------------------------------------------------------- K1 + whole steps vs golden
