@@ -65,7 +65,8 @@ class View(ctypes.Structure):
 class DistArgs(ctypes.Structure):
     """adsb_dist_args (include/adsb200.h): one rank's arguments of the fused distributed sweep"""
     _fields_ = [("rank", c_int), ("nranks", c_int), ("nl", c_int), ("lag", c_int),
-                ("dseg_local", vp), ("x_local", vp), ("dseg_next", vp), ("x_prev", vp), ("error_flag", vp)]
+                ("dseg_local", vp), ("x_local", vp), ("dseg_next", vp), ("x_prev", vp), ("error_flag", vp),
+                ("halo_prev", vp), ("halo_next", vp), ("halo_planes", c_int)]
 
 
 DIST_SENTINEL_WORD = 0x7FF7A5A5   # both 32-bit halves of the sentinel the fused sweep's state arrays hold

@@ -1238,6 +1238,11 @@ int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const ad
     D.dseg_next = d->rank + 1 < d->nranks ? d->dseg_next : nullptr;
     D.x_prev = d->rank > 0 ? d->x_prev : nullptr;
     D.error_flag = d->error_flag;
+    D.halo_prev = d->rank > 0 ? d->halo_prev : nullptr;
+    D.halo_next = d->rank + 1 < d->nranks ? d->halo_next : nullptr;
+    D.halo_planes = d->halo_planes;
+    if ((D.halo_prev && (uintptr_t) D.halo_prev % 16) || (D.halo_next && (uintptr_t) D.halo_next % 16))
+        return fail(ADSB_EINVAL, "dist_sweep_view: halo pointers must be 16 B aligned");
     StageTimer t(c, 1 + axis);
     int rc = -1;
     if (dist_short_chunks() && !g->local_dist.empty())

@@ -99,6 +99,7 @@ struct SweepTileGeom {
     int load_bytes;    // sum of the load boxes (mbarrier transaction count)
     int tile_doubles;  // shared-memory doubles per ring slot
     int nbuf;          // ring depth
+    long long s_row;   // element stride of the rows (fused distributed sweep: halo stores address planes directly)
 };
 // 0: launched; -1: not eligible (caller falls back to launch_sweep); otherwise a cudaError_t.
 // off_in_h / off_out_h: optional host row-offset tables (see adsb_sweep_view); they must be piecewise
@@ -215,6 +216,11 @@ struct SweepDistArgs {
     double* dseg_next;  // state array of rank + 1 (peer pointer), nullptr on the last rank
     double* x_prev;     // state array of rank - 1, nullptr on the first rank
     int* error_flag;
+    // optional: the first / last halo_planes rows of the corrected slab are also stored to these planes (same
+    // line layout as the slab): the neighbours' halo regions
+    double* halo_prev;
+    double* halo_next;
+    int halo_planes;
 };
 // dry_run: only report eligibility (0 / -1), launch nothing
 int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,

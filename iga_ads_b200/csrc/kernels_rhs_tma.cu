@@ -647,6 +647,12 @@ int launch_rhs_tma(const RhsOps& ops, const RhsGeom& g, cudaStream_t st, bool na
     case 3:
         if (variant == 1) return launch_cfg<3, 2, 6, 3, 2>(ops, g, st);
         return launch_cfg<3, 2, 6, 3, 1>(ops, g, st);
+    case 4:
+        if (variant == 1) return launch_cfg<4, 2, 6, 3, 1>(ops, g, st);
+        return launch_cfg<4, 1, 8, 3, 1>(ops, g, st);
+    case 5:
+        if (variant == 1) return launch_cfg<5, 2, 4, 3, 1>(ops, g, st);
+        return launch_cfg<5, 1, 8, 3, 1>(ops, g, st);
     default: return -1;
     }
 }

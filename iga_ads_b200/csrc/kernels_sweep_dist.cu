@@ -304,6 +304,10 @@ __global__ void __launch_bounds__(384, 1)
             if (do2) {
                 const int b = j2 % DIST_NBUF;
                 double* tile = ringD + (size_t) b * tile_doubles;
+                int bx2, m2;
+                tile_of(j2, bx2, m2);
+                const int lanes2 = min(NL, G.L0 - bx2 * NL);
+                const long long hoff2 = (long long) bx2 * NL + (long long) m2 * G.s1_out;  // offset of the tile's lines in a plane
                 const double* dn2 = s_din + (size_t) (j2 % (K + 1)) * KL * NL;
                 double2 st[KC];
 #pragma unroll
@@ -319,6 +323,14 @@ __global__ void __launch_bounds__(384, 1)
                         acc.y = fma(cf[k], st[k].y, acc.y);
                     }
                     *reinterpret_cast<double2*>(tile + (size_t) row * NL + 2 * lp) = acc;
+                    // the slab's first / last planes are the neighbours' halo planes of the next right-hand side:
+                    // store them straight into their state buffers (peer stores; the step's barrier orders them)
+                    if (2 * lp < lanes2) {
+                        if (D.halo_prev && row < D.halo_planes)
+                            *reinterpret_cast<double2*>(D.halo_prev + (long long) row * G.s_row + hoff2 + 2 * lp) = acc;
+                        if (D.halo_next && row >= n - D.halo_planes)
+                            *reinterpret_cast<double2*>(D.halo_next + (long long) (row - (n - D.halo_planes)) * G.s_row + hoff2 + 2 * lp) = acc;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
@@ -450,6 +462,8 @@ int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const Sweep
     Tg.s1_in = Tg.s1_out = G.s1_in;
     Tg.nb0 = (G.L0 + NL - 1) / NL;
     Tg.ntiles = Tg.nb0 * G.L1;
+    Tg.s_row = G.sj_out;
+    if ((D.halo_prev || D.halo_next) && (D.halo_planes < 1 || D.halo_planes > F.n || (G.L0 & 1))) return -1;
     if (!dry_run)
         if (int rc = sweep_strided_maps(G, F.n, NL, nullptr, nullptr, st, Tg)) return rc;
     const int rows_needed = F.SC * CH + F.KL;

@@ -202,6 +202,7 @@ class SlabSim:
             self.nl = nl_env
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.fused = False
+        self.halo_in_kernel = os.environ.get("ADSB_SLAB_HALO_IN_KERNEL", "1") != "0"   # fused sweep stores the halos itself
         self.want_fused = world > 1 and os.environ.get("ADSB_SLAB_FUSED", "1") != "0"
         self.cur = 0
         self.launches = 0
@@ -326,6 +327,16 @@ class SlabSim:
         a.dseg_next = self.peers.ptr(r + 1, "dseg") if r + 1 < S else None
         a.x_prev = self.peers.ptr(r - 1, "x") if r > 0 else None
         a.error_flag = self.err_flag.data_ptr()
+        if self.halo_in_kernel and p > 0:
+            # my first p planes are the upper halo of rank r-1, my last p planes the lower halo of rank r+1
+            name = "h0" if (1 - self.cur) == 0 else "h1"
+            if r > 0:
+                cn = int(self.bounds[r] - self.bounds[r - 1])
+                a.halo_prev = self.peers.ptr(r - 1, name) + 8 * (p + cn) * pl
+            if r + 1 < S:
+                a.halo_next = self.peers.ptr(r + 1, name)
+            a.halo_planes = p
+            self.exchange_bytes += 8 * p * pl * ((r > 0) + (r + 1 < S))
         slot = int(sub.slots[2])
         self.ctx.dist_sweep_view(2, slot, out, self._view_lines(self.cz), a)
         seg = self.seg[slot]
@@ -335,7 +346,8 @@ class SlabSim:
 
     def phase_finish(self, sub=None):
         self.cur = 1 - self.cur
-        self.phase_publish(self.cur)
+        if not self.halo_in_kernel:
+            self.phase_publish(self.cur)
         self._mark("halo")
 
     def phase_local(self, sub):

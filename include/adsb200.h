@@ -293,6 +293,12 @@ typedef struct {
     double* dseg_next;               /* state array of rank + 1 (peer pointer; ignored on the last rank) */
     double* x_prev;                  /* state array of rank - 1 (ignored on the first rank) */
     int* error_flag;                 /* device int, set to 1 when a poll timed out (~2 s); may be NULL */
+    /* optional halo publishing (the right-hand side of the next step needs p planes of each neighbour): the
+     * first halo_planes planes of the finished slab are also stored at halo_prev, the last ones at halo_next
+     * (peer pointers into the neighbours' state buffers, same plane layout as `data`; NULL: skip) */
+    double* halo_prev;
+    double* halo_next;
+    int halo_planes;
 } adsb_dist_args;
 int adsb_dist_sweep_view(adsb_ctx* ctx, int axis, int slot, double* data, const adsb_view* view,
                          const adsb_dist_args* args);
