@@ -38,7 +38,8 @@ namespace adsb {
 
 namespace {
 
-constexpr int DIST_NBUF = 2;  // slots per tile ring
+constexpr int DIST_NBUF = 2;   // slots of the pass-B ring
+constexpr int DIST_NBUF_A = 3; // at most this many slots in the pass-A ring (G.nbuf: 3 when shared memory allows)
 
 // Boundary values validate themselves: a word of the inbox holds the sentinel until the neighbour's store has
 // replaced it.  peek() reads it (possibly still the sentinel), take() spins until the value is there and puts the
@@ -86,8 +87,9 @@ __global__ void __launch_bounds__(384, 1)
     const int tile_doubles = G.tile_doubles;
     const int K = D.lag;
     const int r = D.rank, S = T.S;
+    const int nbA = G.nbuf;
     double* ringA = reinterpret_cast<double*>(smem_raw);
-    double* ringD = ringA + (size_t) DIST_NBUF * tile_doubles;
+    double* ringD = ringA + (size_t) nbA * tile_doubles;
     double* fst = ringD + (size_t) DIST_NBUF * tile_doubles;  // [SC][KL][NL]
     double* bst = fst + SC * KL * NL;                         // [SC][KD][NL]
     double* s_tab = bst + SC * KD * NL;                       // factor tables (blob layout)
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(384, 1)
     double* s_din = s_xf + (K + 1) * KD * NL;                 // [K+1][KL][NL]  din of the tiles between B1 and B2
     double* s_tin = s_din + (K + 1) * KL * NL;                // [KD][NL]
     uint64_t* fullA = reinterpret_cast<uint64_t*>(s_tin + KD * NL);
-    uint64_t* doneA = fullA + DIST_NBUF;
-    uint64_t* fullD = doneA + DIST_NBUF;
+    uint64_t* doneA = fullA + DIST_NBUF_A;
+    uint64_t* fullD = doneA + DIST_NBUF_A;
     uint64_t* doneD = fullD + DIST_NBUF;
     uint64_t* tabbar = doneD + DIST_NBUF;
     uint64_t* xf_full = tabbar + 1;        // [K+1]
@@ -108,9 +110,11 @@ __global__ void __launch_bounds__(384, 1)
 
     pdl_launch();
     if (tid == 0) {
-        for (int b = 0; b < DIST_NBUF; ++b) {
+        for (int b = 0; b < DIST_NBUF_A; ++b) {
             mbar_init(&fullA[b], 1);
             mbar_init(&doneA[b], 1);
+        }
+        for (int b = 0; b < DIST_NBUF; ++b) {
             mbar_init(&fullD[b], 1);
             mbar_init(&doneD[b], 1);
         }
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(384, 1)
     {
         const int nthr = (int) blockDim.x;
         const int pad0 = n * NL, pad = tile_doubles - pad0;
-        for (int i = tid; i < 2 * DIST_NBUF * pad; i += nthr) ringA[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
+        for (int i = tid; i < (nbA + DIST_NBUF) * pad; i += nthr) ringA[(size_t) (i / pad) * tile_doubles + pad0 + i % pad] = 0.0;
         const int a = D.row_base;
         for (int i = tid; i < n * KC; i += nthr) s_cf[i] = T.cf[(size_t) a * KC + i];
         for (int i = tid; i < KL * KL; i += nthr) s_E[i] = T.E[(size_t) r * KL * KL + i];
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(384, 1)
             auto load = [&](int i) {
                 int bx, m;
                 tile_of(i, bx, m);
-                const int b = i % DIST_NBUF;
+                const int b = i % nbA;
                 double* dst = ringA + (size_t) b * tile_doubles;
                 mbar_expect_tx(&fullA[b], (uint32_t) G.load_bytes);
                 for (int k = 0; k < G.nbox_in; ++k) tma_load_3d(dst + G.row0_in[k] * NL, maps + k, bx * NL, 0, m, &fullA[b]);
@@ -161,18 +165,20 @@ __global__ void __launch_bounds__(384, 1)
             auto store = [&](int i) {
                 int bx, m;
                 tile_of(i, bx, m);
-                const double* src = ringA + (size_t) (i % DIST_NBUF) * tile_doubles;
+                const double* src = ringA + (size_t) (i % nbA) * tile_doubles;
                 for (int k = 0; k < G.nbox_out; ++k)
                     tma_store_3d(maps + G.nbox_in + k, bx * NL, 0, m, src + G.row0_out[k] * NL);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             };
-            for (int i = 0; i < DIST_NBUF - 1 && i < my_count; ++i) load(i);
+            for (int i = 0; i < nbA - 1 && i < my_count; ++i) load(i);
             for (int j = 0; j < my_count; ++j) {
-                if (j + DIST_NBUF - 1 < my_count) {
+                if (j + nbA - 1 < my_count) {
+                    // the slot of tile j-1 is reloaded: its store must have read shared memory (with three slots
+                    // the store before it, so the newest store may still be draining)
                     if (j >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    load(j + DIST_NBUF - 1);
+                    load(j + nbA - 1);
                 }
-                mbar_wait(&doneA[j % DIST_NBUF], (uint32_t) ((j / DIST_NBUF) & 1));
+                mbar_wait(&doneA[j % nbA], (uint32_t) ((j / nbA) & 1));
                 store(j);
                 // all but the two most recent stores have reached memory: tiles 0 .. j-2 may be read back
                 asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
@@ -357,9 +363,9 @@ __global__ void __launch_bounds__(384, 1)
     const int c = min(tid / NLt, SC - 1);  // padding threads shadow the last chunk (identical values)
     const int j0 = c * CH;
     for (int it = 0; it < my_count; ++it) {
-        const int b = it % DIST_NBUF;
+        const int b = it % nbA;
         double* tile = ringA + (size_t) b * tile_doubles;
-        mbar_wait(&fullA[b], (uint32_t) ((it / DIST_NBUF) & 1));
+        mbar_wait(&fullA[b], (uint32_t) ((it / nbA) & 1));
         double v[RL][CH + KL];
         {
             const double* mine = tile + (size_t) j0 * NL + 2 * tx;
@@ -468,12 +474,15 @@ int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const Sweep
         if (int rc = sweep_strided_maps(G, F.n, NL, nullptr, nullptr, st, Tg)) return rc;
     const int rows_needed = F.SC * CH + F.KL;
     Tg.tile_doubles = (rows_needed * NL + 15) & ~15;
-    Tg.nbuf = DIST_NBUF;
     const int KC = T.KD + T.KL, K = D.lag;
-    const size_t doubles = (size_t) 2 * DIST_NBUF * Tg.tile_doubles + (size_t) F.SC * (F.KL + F.KD) * NL + F.blob_doubles +
+    const size_t rest = (size_t) F.SC * (F.KL + F.KD) * NL + F.blob_doubles + ((F.n * KC + 1) & ~1) + ((T.KL * T.KL + 1) & ~1) +
+                        ((T.KD * T.KL + 1) & ~1) + (size_t) (K + 1) * T.KD * NL + (size_t) (K + 1) * T.KL * NL + (size_t) T.KD * NL;
+    const size_t fixed_b = rest * 8 + (2 * DIST_NBUF_A + 2 * DIST_NBUF + 1 + 2 * (K + 1)) * 8 + 64;
+    Tg.nbuf = (fixed_b + (size_t) (DIST_NBUF_A + DIST_NBUF) * Tg.tile_doubles * 8 <= 226 * 1024) ? DIST_NBUF_A : 2;
+    const size_t doubles = (size_t) (Tg.nbuf + DIST_NBUF) * Tg.tile_doubles + (size_t) F.SC * (F.KL + F.KD) * NL + F.blob_doubles +
                            ((F.n * KC + 1) & ~1) + ((T.KL * T.KL + 1) & ~1) + ((T.KD * T.KL + 1) & ~1) +
                            (size_t) (K + 1) * T.KD * NL + (size_t) (K + 1) * T.KL * NL + (size_t) T.KD * NL;
-    const size_t smem = doubles * 8 + (4 * DIST_NBUF + 1 + 2 * (K + 1)) * 8 + 64;
+    const size_t smem = doubles * 8 + (2 * DIST_NBUF_A + 2 * DIST_NBUF + 1 + 2 * (K + 1)) * 8 + 64;
     if (smem > 226 * 1024) return -1;
     dist_kern_t k = pick(F.KL, F.piv != 0, NL, CH);
     if (!k) return -1;
