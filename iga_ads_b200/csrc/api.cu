@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -971,6 +972,45 @@ int adsb_project_init(adsb_ctx* c, int state, int dst) {
     cudaError_t e = (cudaError_t) launch_project(state, A, c->buf[dst], c->lo, c->cnt, c->stream, c->pitch0());
     if (e != cudaSuccess) return cuda_fail(e, "project kernel");
     c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_norm(adsb_ctx* c, int b, int kind, int ref, double t, const double* ref_values, double* out2) {
+    if (!c || !out2) return fail(ADSB_EINVAL, "norm: null argument");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "norm: buffer not allocated");
+    if (kind < 0 || kind > 1 || ref < 0 || ref > 2) return fail(ADSB_EINVAL, "norm: kind is 0 (L2) or 1 (H1), ref 0..2");
+    if (ref == 2 && (!ref_values || kind != 0)) return fail(ADSB_EINVAL, "norm: tabulated reference values give the L2 error only");
+    for (int d = 0; d < c->ndim; ++d)
+        if (c->cnt[d] != c->ng[d]) return fail(ADSB_ESTATE, "norm: the context must own the whole domain");
+    if (int rc = select_device(c)) return rc;
+    QuadAxes A;
+    if (int rc = quad_axes(c, A)) return rc;
+    const long long np = norm_partial_doubles(A);
+    size_t ntab = 0;
+    if (ref == 2) {
+        ntab = 1;
+        for (int d = 0; d < c->ndim; ++d) ntab *= (size_t) A.ne[d] * A.q[d];
+    }
+    double* scratch = nullptr;
+    CU(cudaMalloc((void**) &scratch, ((size_t) np + 2 + ntab) * sizeof(double)));
+    double* d_out = scratch + np;
+    double* d_tab = ntab ? d_out + 2 : nullptr;
+    cudaError_t e = cudaSuccess;
+    if (ntab) e = cudaMemcpyAsync(d_tab, ref_values, ntab * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    {
+        StageTimer tm(c, 4);
+        if (e == cudaSuccess)
+            e = (cudaError_t) launch_norm(A, c->buf[b], c->pitch0(), c->pitch0() * c->cnt[1], kind, ref, t, d_tab, scratch, d_out,
+                                          c->stream);
+    }
+    double h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "norm kernels");
+    c->launches += 2;
+    out2[0] = std::sqrt(h[0]);
+    out2[1] = std::sqrt(h[1]);
     return ADSB_OK;
 }
 

@@ -226,6 +226,13 @@ struct SweepDistArgs {
 int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
                       cudaStream_t st, bool dry_run = false);
 
+// Norms / errors by element quadrature (kernels_norm.cu).  partial: norm_partial_doubles() doubles of scratch;
+// out: 2 doubles on the device (sum of N(u_h - ref) w J, sum of N(ref) w J).  h1: add the gradient terms;
+// ref: 0 none, 1 validation solution at time t, 2 tabulated values `tab` at the quadrature points (x fastest).
+long long norm_partial_doubles(const QuadAxes& A);
+int launch_norm(const QuadAxes& A, const double* u, long long s1, long long s2, int h1, int ref, double t,
+                const double* tab, double* partial, double* out, cudaStream_t st);
+
 // vnx > 0: `values` are the first elements of a tensor with x rows of vnx doubles, vpitch apart (else dense)
 int launch_set_plane(double* t, const long long s[3], const int n[3], int axis, int idx,
                      const double* values, cudaStream_t st, int vnx = 0, long long vpitch = 0);

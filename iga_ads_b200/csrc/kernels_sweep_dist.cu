@@ -140,10 +140,11 @@ __global__ void __launch_bounds__(384, 1)
 
     const int my_count = (G.ntiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(G.maps);
+    // the lines are numbered flat (launch_sweep_dist insists on contiguous lines, L1 == 1): tile i of this CTA
+    // starts at line (blockIdx.x + i * gridDim.x) * NL -- no divisions anywhere in the loops
     auto tile_of = [&](int i, int& bx, int& m) {
-        const int t = blockIdx.x + i * gridDim.x;
-        bx = t % G.nb0;
-        m = t / G.nb0;
+        bx = blockIdx.x + i * gridDim.x;
+        m = 0;
     };
     const long long L = (long long) G.L0 * G.L1;
 
@@ -233,20 +234,18 @@ __global__ void __launch_bounds__(384, 1)
         auto slot1 = [&](int j, int v) -> double* {
             const int i = t + v * NB;
             if (r == 0 || j < 0 || j >= my_count || i >= KL * NL) return nullptr;
-            int bx, m;
-            tile_of(j, bx, m);
+            const long long l0 = (long long) (blockIdx.x + j * gridDim.x) * NL;
             const int kk = i / NL, ln = i % NL;
-            if (ln >= min(NL, G.L0 - bx * NL)) return nullptr;
-            return D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + (long long) bx * NL + (long long) m * G.L0 + ln;
+            if (l0 + ln >= G.L0) return nullptr;
+            return D.dseg_local + ((size_t) (r - 1) * KL + kk) * L + l0 + ln;
         };
         auto slot2 = [&](int j, int v) -> double* {
             const int i = t + v * NB;
             if (r + 1 >= S || j < 0 || j >= my_count || i >= KD * NL) return nullptr;
-            int bx, m;
-            tile_of(j, bx, m);
+            const long long l0 = (long long) (blockIdx.x + j * gridDim.x) * NL;
             const int ii = i / NL, ln = i % NL;
-            if (ln >= min(NL, G.L0 - bx * NL)) return nullptr;
-            return D.x_local + ((size_t) (r + 1) * KD + ii) * L + (long long) bx * NL + (long long) m * G.L0 + ln;
+            if (l0 + ln >= G.L0) return nullptr;
+            return D.x_local + ((size_t) (r + 1) * KD + ii) * L + l0 + ln;
         };
         // the loads of iteration jj + 1 are issued during iteration jj, so their latency (and, mostly, the wait
         // for the neighbour) is off the critical path
@@ -261,14 +260,16 @@ __global__ void __launch_bounds__(384, 1)
             double* a = slot2(-K, v);
             pre2[v] = a ? peek_value(a) : 0ull;
         }
+        int s1 = 0, use1 = 0;  // hand-over ring slot of tile j1 (= j1 % (K+1)) and how often it has been used
         for (int jj = 0; jj < my_count + K; ++jj) {
             const int j1 = jj, j2 = jj - K;
+            const int s2 = (s1 + 1 > K) ? 0 : s1 + 1;  // slot of tile j2 = j1 - K  ==  (j1 + 1) mod (K+1)
             const bool do1 = j1 < my_count, do2 = j2 >= 0;
             int bx1 = 0, m1 = 0;
             if (do1) tile_of(j1, bx1, m1);
             const long long line1 = (long long) bx1 * NL + (long long) m1 * G.L0;
             const int lanes1 = min(NL, G.L0 - bx1 * NL);
-            double* dn1 = s_din + (size_t) (j1 % (K + 1)) * KL * NL;
+            double* dn1 = s_din + (size_t) s1 * KL * NL;
             // ---- the boundary values both stages need (zero where there is no neighbour / no line)
 #pragma unroll
             for (int v = 0; v < NV1; ++v) {
@@ -290,12 +291,12 @@ __global__ void __launch_bounds__(384, 1)
                 double* nx = slot2(j2 + 1, v);
                 pre2[v] = nx ? peek_value(nx) : 0ull;
             }
-            if (do1) mbar_wait(&xf_full[j1 % (K + 1)], (uint32_t) ((j1 / (K + 1)) & 1));
+            if (do1) mbar_wait(&xf_full[s1], (uint32_t) (use1 & 1));
             if (do2) mbar_wait(&fullD[j2 % DIST_NBUF], (uint32_t) ((j2 / DIST_NBUF) & 1));
             group_sync(2, NB);
             // ---- B1: X = xhat[first KD rows] + XiF din  -> previous rank
             if (do1 && D.x_prev) {
-                const double* xf = s_xf + (size_t) (j1 % (K + 1)) * KD * NL;
+                const double* xf = s_xf + (size_t) s1 * KD * NL;
                 for (int i = t; i < KD * NL; i += NB) {
                     const int ii = i / NL, ln = i % NL;
                     if (ln < lanes1) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(384, 1)
                 tile_of(j2, bx2, m2);
                 const int lanes2 = min(NL, G.L0 - bx2 * NL);
                 const long long hoff2 = (long long) bx2 * NL + (long long) m2 * G.s1_out;  // offset of the tile's lines in a plane
-                const double* dn2 = s_din + (size_t) (j2 % (K + 1)) * KL * NL;
+                const double* dn2 = s_din + (size_t) s2 * KL * NL;
                 double2 st[KC];
 #pragma unroll
                 for (int k = 0; k < KD; ++k) st[k] = *reinterpret_cast<const double2*>(s_tin + k * NL + 2 * lp);
@@ -329,21 +330,30 @@ __global__ void __launch_bounds__(384, 1)
                         acc.y = fma(cf[k], st[k].y, acc.y);
                     }
                     *reinterpret_cast<double2*>(tile + (size_t) row * NL + 2 * lp) = acc;
-                    // the slab's first / last planes are the neighbours' halo planes of the next right-hand side:
-                    // store them straight into their state buffers (peer stores; the step's barrier orders them)
-                    if (2 * lp < lanes2) {
-                        if (D.halo_prev && row < D.halo_planes)
-                            *reinterpret_cast<double2*>(D.halo_prev + (long long) row * G.s_row + hoff2 + 2 * lp) = acc;
-                        if (D.halo_next && row >= n - D.halo_planes)
-                            *reinterpret_cast<double2*>(D.halo_next + (long long) (row - (n - D.halo_planes)) * G.s_row + hoff2 + 2 * lp) = acc;
+                }
+                // the slab's first / last planes are the neighbours' halo planes of the next right-hand side: the
+                // thread that corrected such a row stores it straight into their state buffers (peer stores; the
+                // step's barrier orders them)
+                if ((D.halo_prev || D.halo_next) && 2 * lp < lanes2) {
+                    const int hp = D.halo_planes;
+                    for (int h = 0; h < 2 * hp; ++h) {
+                        const int row = h < hp ? h : n - 2 * hp + h;
+                        double* dst = h < hp ? D.halo_prev : D.halo_next;
+                        if (row % RG == rg && dst)
+                            *reinterpret_cast<double2*>(dst + (long long) (h < hp ? h : h - hp) * G.s_row + hoff2 + 2 * lp) =
+                                *reinterpret_cast<const double2*>(tile + (size_t) row * NL + 2 * lp);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
             group_sync(2, NB);
             if (t == 0) {
-                if (do1) mbar_arrive(&xf_free[j1 % (K + 1)]);
+                if (do1) mbar_arrive(&xf_free[s1]);
                 if (do2) mbar_arrive(&doneD[j2 % DIST_NBUF]);
+            }
+            if (++s1 > K) {
+                s1 = 0;
+                ++use1;
             }
         }
         return;
@@ -362,10 +372,10 @@ __global__ void __launch_bounds__(384, 1)
     const int tx = tid % NLt;
     const int c = min(tid / NLt, SC - 1);  // padding threads shadow the last chunk (identical values)
     const int j0 = c * CH;
+    int xs = 0, use = 0, b = 0, useA = 0;  // hand-over ring slot / use count; pass-A ring slot / use count
     for (int it = 0; it < my_count; ++it) {
-        const int b = it % nbA;
         double* tile = ringA + (size_t) b * tile_doubles;
-        mbar_wait(&fullA[b], (uint32_t) ((it / nbA) & 1));
+        mbar_wait(&fullA[b], (uint32_t) (useA & 1));
         double v[RL][CH + KL];
         {
             const double* mine = tile + (size_t) j0 * NL + 2 * tx;
@@ -385,7 +395,6 @@ __global__ void __launch_bounds__(384, 1)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // slot of the hand-over ring: free once group B has used its previous content
-        const int xs = it % (K + 1), use = it / (K + 1);
         if (use > 0) mbar_wait(&xf_free[xs], (uint32_t) ((use - 1) & 1));
         sweep_sync(ncons);
         // the tile is final for pass A: its first KD rows go to group B, Dseg to the next rank
@@ -410,6 +419,14 @@ __global__ void __launch_bounds__(384, 1)
         if (tid == 0) {
             mbar_arrive(&doneA[b]);
             mbar_arrive(&xf_full[xs]);
+        }
+        if (++xs > K) {
+            xs = 0;
+            ++use;
+        }
+        if (++b >= nbA) {
+            b = 0;
+            ++useA;
         }
     }
 }
@@ -455,6 +472,7 @@ int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const Sweep
     if (T.KL != F.KL || T.KD != F.KD) return -1;             // the slab's own factor needs the same kernel variant
     if (G.in != G.out || G.sj_in != G.sj_out || G.s1_in != G.s1_out) return -1;  // in place
     if (NL != 16 && NL != 32 && NL != 64) return -1;
+    if (G.L1 != 1) return -1;  // contiguous lines, numbered flat (the z lines of an x-fastest tensor without row gaps)
     const int NLt = NL / SWEEP_RL;
     const int ncons = (NLt * F.SC + 31) / 32 * 32;
     if (ncons > 192 || NLt > DIST_NB || DIST_NB % NLt != 0 || D.lag < 1 || D.lag > 16) return -1;

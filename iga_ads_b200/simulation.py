@@ -121,6 +121,19 @@ class Context:
     def project_init(self, state, dst):
         check(self.lib.adsb_project_init(self.h, state, dst))
 
+    def norm(self, buf, kind="L2", ref=0, t=0.0, ref_values=None):
+        """(norm of u_h - ref, norm of ref) by element quadrature: basic_simulation_Nd::norm / error
+        (include/ads/simulation/basic_simulation_3d.hpp:281-398).  ref: 0 none, 1 validation solution at time t,
+        2 `ref_values` tabulated at the quadrature points (L2 only)"""
+        out = np.zeros(2)
+        tab = None
+        if ref_values is not None:
+            tab = np.ascontiguousarray(ref_values, dtype=np.float64).ravel()
+            ref = 2
+        check(self.lib.adsb_norm(self.h, buf, {"L2": 0, "H1": 1}[kind], ref, float(t), d_(tab) if tab is not None else None,
+                                 d_(out)))
+        return float(out[0]), float(out[1])
+
     def solve(self, buf, slots=None):
         s = np.array(list(slots or ()) + [0] * (3 - len(slots or ())), dtype=np.int32)
         check(self.lib.adsb_solve(self.h, buf, i_(s)))

@@ -176,6 +176,16 @@ int adsb_load_tensor(adsb_ctx* ctx, int source, int with_test_function, int dst_
  * (examples/implicit/implicit.hpp:38-43), 2 constant one. */
 int adsb_project_init(adsb_ctx* ctx, int state, int dst_buf);
 
+/* ---- norms and errors of the spline solution by element quadrature (a diagnostic outside the step)
+ * Replaces basic_simulation_2d/3d::normL2 / normH1 / errorL2 / errorH1
+ * (include/ads/simulation/basic_simulation_3d.hpp:281-398; basic_simulation_2d.hpp likewise):
+ *   out2[0] = sqrt( sum_e sum_q N(u_h(x_q) - ref(x_q)) w J ),   out2[1] = sqrt( sum_e sum_q N(ref(x_q)) w J )
+ * kind 0: N = val^2 (L2); 1: val^2 + |grad|^2 (H1).  ref 0: none (out2[0] is the norm of u_h); 1: the
+ * validation solution sin(pi x) sin(pi y) [sin(pi z)] exp(-d pi^2 t) (examples/validation/validation.hpp:45-55);
+ * 2: values tabulated by the caller at the quadrature points, x fastest: ref_values[(ex*q+kx) + nqx*((ey*q+ky) +
+ * nqy*(ez*q+kz))] (host memory; L2 only).  The context must own the whole domain; the call synchronises. */
+int adsb_norm(adsb_ctx* ctx, int buf, int kind, int ref, double t, const double* ref_values, double* out2);
+
 /* ---- ADS solve: one batched banded forward/back substitution per axis, in place.
  * Replaces ads::ads_solve(rhs, buffer, dims...) (include/ads/solver.hpp:35-41,:148-160,:222-226)
  * i.e. 3 x { lin::solve_with_factorized -> dgbtrs_ (include/ads/lin/band_solve.hpp:21-31) +

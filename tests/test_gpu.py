@@ -572,3 +572,56 @@ def test_device_projection_and_shipped_runs_vs_reference_golden(golden):
         if ns <= 5:
             sim.advance(ns)
             assert rel_l2(sim.state(), g[tag + "_shipped"]) < (ns + 1) * tol, (tag, "shipped run")
+
+
+# ---------------------------------------------------------------------- norms / errors on the device
+def _host_norm_terms(sim, u, t=None):
+    """numpy restatement of basic_simulation_Nd::norm / error (include/ads/simulation/basic_simulation_3d.hpp:
+    281-398): u_h and its gradient at every quadrature point, weights, points; returns (vals[4], wJ, pts)"""
+    mats = []
+    for d in sim.dims:
+        tb, ne, q, p = d.basis, d.elements, d.quad_order, d.p
+        V, D = np.zeros((ne * q, d.dofs())), np.zeros((ne * q, d.dofs()))
+        for e in range(ne):
+            for k in range(q):
+                V[e * q + k, e:e + p + 1] = tb["b"][e, k, 0]
+                D[e * q + k, e:e + p + 1] = tb["b"][e, k, 1]
+        mats.append((V, D, (tb["w"][None, :] * tb["J"][:, None]).ravel(), tb["x"].ravel()))
+    if len(mats) == 2:
+        (Vx, Dx, wx, px), (Vy, Dy, wy, py) = mats
+        U = u.reshape(sim.dims[1].dofs(), sim.dims[0].dofs())
+        vals = [Vy @ U @ Vx.T, Vy @ U @ Dx.T, Dy @ U @ Vx.T, 0.0]
+        return vals, wy[:, None] * wx[None, :], (px[None, :], py[:, None], 0.0)
+    (Vx, Dx, wx, px), (Vy, Dy, wy, py), (Vz, Dz, wz, pz) = mats
+    U = u.reshape(sim.dims[2].dofs(), sim.dims[1].dofs(), sim.dims[0].dofs())
+    ev = lambda A, B, C: np.einsum("ck,bj,ai,kji->cba", A, B, C, U, optimize=True)
+    vals = [ev(Vz, Vy, Vx), ev(Vz, Vy, Dx), ev(Vz, Dy, Vx), ev(Dz, Vy, Vx)]
+    return vals, wz[:, None, None] * wy[None, :, None] * wx[None, None, :], (px[None, None, :], py[None, :, None], pz[:, None, None])
+
+
+@pytest.mark.parametrize("name,p,ne", [("heat_2d", 3, 37), ("heat_2d", 2, 150), ("heat_3d", 2, 14), ("scalability_3d", 4, 9)])
+def test_device_norms_and_errors(name, p, ne):
+    """adsb_norm: L2 / H1 norms of u_h, errors against the validation solution and against tabulated values"""
+    sim = make_problem(name, p, ne, 1e-5)
+    u = synthetic_state(sim.shape())
+    sim.set_state(u)
+    vals, wJ, (x, y, z) = _host_norm_terms(sim, u)
+    d3 = len(sim.dims) == 3
+    l2 = np.sqrt(np.sum(vals[0] ** 2 * wJ))
+    h1 = np.sqrt(np.sum((vals[0] ** 2 + vals[1] ** 2 + vals[2] ** 2 + (vals[3] ** 2 if d3 else 0.0)) * wJ))
+    assert abs(sim.ctx.norm(U, "L2")[0] - l2) < 1e-13 * l2
+    assert abs(sim.ctx.norm(U, "H1")[0] - h1) < 1e-13 * h1
+    t = 0.013
+    sc = np.exp(-(3 if d3 else 2) * np.pi ** 2 * t)
+    sz, cz = (np.sin(np.pi * z), np.cos(np.pi * z)) if d3 else (1.0, 0.0)
+    r = [sc * np.sin(np.pi * x) * np.sin(np.pi * y) * sz, sc * np.pi * np.cos(np.pi * x) * np.sin(np.pi * y) * sz,
+         sc * np.pi * np.sin(np.pi * x) * np.cos(np.pi * y) * sz, sc * np.pi * np.sin(np.pi * x) * np.sin(np.pi * y) * cz]
+    e_l2 = np.sqrt(np.sum((vals[0] - r[0]) ** 2 * wJ))
+    e_h1 = np.sqrt(np.sum(sum((vals[k] - r[k]) ** 2 for k in range(4 if d3 else 3)) * wJ))
+    n_h1 = np.sqrt(np.sum(sum(np.broadcast_to(r[k], wJ.shape) ** 2 for k in range(4 if d3 else 3)) * wJ))
+    got_l2, got_h1 = sim.ctx.norm(U, "L2", ref=1, t=t), sim.ctx.norm(U, "H1", ref=1, t=t)
+    assert abs(got_l2[0] - e_l2) < 1e-12 * e_l2 and abs(got_h1[0] - e_h1) < 1e-12 * e_h1
+    assert abs(got_h1[1] - n_h1) < 1e-12 * n_h1
+    tab = np.broadcast_to(np.cos(3 * x) * (y + 0.5) * (1 + z), wJ.shape).copy()
+    e_tab = np.sqrt(np.sum((vals[0] - tab) ** 2 * wJ))
+    assert abs(sim.ctx.norm(U, "L2", ref_values=tab)[0] - e_tab) < 1e-12 * e_tab
