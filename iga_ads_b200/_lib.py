@@ -113,6 +113,7 @@ _SIGNATURES = {
     "adsb_compute_rhs": (c_int, [vp, ctypes.POINTER(Form), c_int, c_int]),
     "adsb_load_tensor": (c_int, [vp, c_int, c_int, c_int]),
     "adsb_project_init": (c_int, [vp, c_int, c_int]),
+    "adsb_sample": (c_int, [vp, c_int, ip, ctypes.POINTER(dp), ctypes.POINTER(dp), dp]),
     "adsb_norm": (c_int, [vp, c_int, c_int, c_int, c_dbl, dp, dp]),
     "adsb_solve": (c_int, [vp, c_int, ip]),
     "adsb_sweep": (c_int, [vp, c_int, c_int, c_int]),

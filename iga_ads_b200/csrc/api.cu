@@ -975,6 +975,60 @@ int adsb_project_init(adsb_ctx* c, int state, int dst) {
     return ADSB_OK;
 }
 
+int adsb_sample(adsb_ctx* c, int b, const int* npts, const double* const* points, const double* const* knots,
+                double* out) {
+    if (!c || !npts || !points || !knots || !out) return fail(ADSB_EINVAL, "sample: null argument");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "sample: buffer not allocated");
+    for (int d = 0; d < c->ndim; ++d) {
+        if (c->cnt[d] != c->ng[d]) return fail(ADSB_ESTATE, "sample: the context must own the whole domain");
+        if (!c->ax[d].tables) return fail(ADSB_ESTATE, "sample: axis tables not uploaded");
+        if (npts[d] < 1 || !points[d] || !knots[d]) return fail(ADSB_EINVAL, "sample: bad points");
+    }
+    if (int rc = select_device(c)) return rc;
+    int p[3] = {0, 0, 0};
+    int* d_first[3] = {nullptr, nullptr, nullptr};
+    double* d_val[3] = {nullptr, nullptr, nullptr};
+    std::vector<void*> tmp;
+    auto cleanup = [&] {
+        for (void* q : tmp) cudaFree(q);
+    };
+    size_t total = 1;
+    for (int d = 0; d < c->ndim; ++d) {
+        const AxisData& ax = c->ax[d];
+        p[d] = ax.p;
+        const int ks = ax.elements + 2 * ax.p + 1;
+        std::vector<int> first(npts[d]);
+        std::vector<double> val((size_t) npts[d] * (ax.p + 1));
+        for (int i = 0; i < npts[d]; ++i) {
+            // bspline::eval: span of the point, the p+1 non-zero functions start at DOF span - p
+            const int span = find_span(points[d][i], knots[d], ks, ax.p);
+            first[i] = span - ax.p;
+            basis_ders(span, points[d][i], knots[d], ax.p, 0, &val[(size_t) i * (ax.p + 1)]);
+        }
+        if (int rc = upload_vec(first, 0, &d_first[d], &tmp)) { cleanup(); return rc; }
+        if (int rc = upload_vec(val, 0, &d_val[d], &tmp)) { cleanup(); return rc; }
+        total *= (size_t) npts[d];
+    }
+    double* d_out = nullptr;
+    if (cudaMalloc((void**) &d_out, total * sizeof(double)) != cudaSuccess) {
+        cleanup();
+        return fail(ADSB_ENOMEM, "sample: out of device memory");
+    }
+    tmp.push_back(d_out);
+    cudaError_t e;
+    {
+        StageTimer tm(c, 4);
+        e = (cudaError_t) launch_sample(c->ndim, npts, p, d_first, d_val, c->buf[b], c->pitch0(), c->pitch0() * c->cnt[1], d_out,
+                                        c->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) return cuda_fail(e, "sample kernel");
+    c->launches++;
+    return ADSB_OK;
+}
+
 int adsb_norm(adsb_ctx* c, int b, int kind, int ref, double t, const double* ref_values, double* out2) {
     if (!c || !out2) return fail(ADSB_EINVAL, "norm: null argument");
     if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "norm: buffer not allocated");

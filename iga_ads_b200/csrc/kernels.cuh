@@ -226,6 +226,11 @@ struct SweepDistArgs {
 int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
                       cudaStream_t st, bool dry_run = false);
 
+// Spline values at a tensor-product grid of points (kernels_quad.cu): per axis the first DOF of every point's
+// span and its p+1 basis values (device arrays); out[i + n0*(j + n1*k)].
+int launch_sample(int ndim, const int* npts, const int* p, const int* const* first, const double* const* val,
+                  const double* u, long long s1, long long s2, double* out, cudaStream_t st);
+
 // Norms / errors by element quadrature (kernels_norm.cu).  partial: norm_partial_doubles() doubles of scratch;
 // out: 2 doubles on the device (sum of N(u_h - ref) w J, sum of N(ref) w J).  h1: add the gradient terms;
 // ref: 0 none, 1 validation solution at time t, 2 tabulated values `tab` at the quadrature points (x fastest).

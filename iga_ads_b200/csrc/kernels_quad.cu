@@ -156,4 +156,57 @@ int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int el
     return (int) cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Output sampling: the spline at a tensor-product grid of points (output_manager<2/3>::write / evaluate,
+// include/ads/output_manager.hpp:66-73,:101-118 with bspline::eval, include/ads/bspline/eval.hpp:161-192).
+// The host finds the span of every point and evaluates the p+1 non-zero basis functions per axis
+// (find_span / eval_basis, O(points * p^2)); a thread per output point does the (p+1)^d contraction in the
+// reference's loop order (ix outermost) and association ((u * bx) * by) * bz, without contraction to FMA.
+namespace {
+struct SampleAxes {
+    int ndim;
+    int npts[3], p[3];
+    const int* first[3];    // [npts] first DOF of the point's span (span - p)
+    const double* val[3];   // [npts][p+1]
+};
+__global__ void sample_kernel(const SampleAxes A, const double* __restrict__ u, long long s1, long long s2,
+                              double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= A.npts[0]) return;
+    const bool d3 = A.ndim == 3;
+    const int p0 = A.p[0], p1 = A.p[1], p2 = d3 ? A.p[2] : 0;
+    const double* bx = A.val[0] + (size_t) i * (p0 + 1);
+    const double* by = A.val[1] + (size_t) j * (p1 + 1);
+    const double* bz = d3 ? A.val[2] + (size_t) k * (p2 + 1) : nullptr;
+    const double* base = u + A.first[0][i] + s1 * A.first[1][j] + (d3 ? s2 * A.first[2][k] : 0);
+    double value = 0.0;
+    for (int ix = 0; ix <= p0; ++ix)
+        for (int iy = 0; iy <= p1; ++iy)
+            for (int iz = 0; iz <= p2; ++iz) {
+                double t = __dmul_rn(__dmul_rn(base[ix + s1 * iy + s2 * iz], bx[ix]), by[iy]);
+                if (d3) t = __dmul_rn(t, bz[iz]);
+                value = __dadd_rn(value, t);
+            }
+    out[i + (long long) A.npts[0] * (j + (long long) A.npts[1] * k)] = value;
+}
+}  // namespace
+
+int launch_sample(int ndim, const int* npts, const int* p, const int* const* first, const double* const* val,
+                  const double* u, long long s1, long long s2, double* out, cudaStream_t st) {
+    SampleAxes A{};
+    A.ndim = ndim;
+    for (int d = 0; d < 3; ++d) {
+        A.npts[d] = d < ndim ? npts[d] : 1;
+        A.p[d] = d < ndim ? p[d] : 0;
+        A.first[d] = d < ndim ? first[d] : nullptr;
+        A.val[d] = d < ndim ? val[d] : nullptr;
+    }
+    if (A.npts[1] > 65535 || A.npts[2] > 65535) return (int) cudaErrorInvalidValue;
+    dim3 block(128), grid((A.npts[0] + 127) / 128, A.npts[1], A.npts[2]);
+    sample_kernel<<<grid, block, 0, st>>>(A, u, s1, ndim == 3 ? s2 : 0, out);
+    return (int) cudaGetLastError();
+}
+
 }  // namespace adsb

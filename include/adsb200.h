@@ -176,6 +176,17 @@ int adsb_load_tensor(adsb_ctx* ctx, int source, int with_test_function, int dst_
  * (examples/implicit/implicit.hpp:38-43), 2 constant one. */
 int adsb_project_init(adsb_ctx* ctx, int state, int dst_buf);
 
+/* ---- output sampling: the spline on a tensor-product grid of points
+ * Replaces output_manager<2/3>::write / evaluate (include/ads/output_manager.hpp:66-73,:101-118), i.e.
+ * bspline::eval at every point (include/ads/bspline/eval.hpp:161-192): points[d] are npts[d] coordinates along
+ * axis d (the reference uses linspace(a, b, intervals): intervals + 1 points), knots[d] the axis' knot vector
+ * (adsb_knots).  out (host) receives npts[0]*npts[1][*npts[2]] values, first index fastest -- the order the
+ * reference's writers print them in (include/ads/output/vtk.hpp:45-82, gnuplot.hpp:45-56).  The spans and basis
+ * values are found on the host exactly as the reference does, the contraction runs on the device in the
+ * reference's order.  The context must own the whole domain; the call synchronises. */
+int adsb_sample(adsb_ctx* ctx, int buf, const int* npts, const double* const* points, const double* const* knots,
+                double* out);
+
 /* ---- norms and errors of the spline solution by element quadrature (a diagnostic outside the step)
  * Replaces basic_simulation_2d/3d::normL2 / normH1 / errorL2 / errorH1
  * (include/ads/simulation/basic_simulation_3d.hpp:281-398; basic_simulation_2d.hpp likewise):
