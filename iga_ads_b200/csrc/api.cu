@@ -644,6 +644,8 @@ int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int 
     if (p < 1 || p > 5) return fail(ADSB_EINVAL, "set_axis_tables: device kernels are built for 1 <= p <= 5");
     if (elements + p != c->ng[axis]) return fail(ADSB_EINVAL, "set_axis_tables: elements + p != n_global[axis]");
     if (ders < 1) return fail(ADSB_EINVAL, "set_axis_tables: first derivatives are required");
+    if (!b_flat || !xq || !w || !J || !first_dof || q < 1 || elements < 1)
+        return fail(ADSB_EINVAL, "set_axis_tables: null table / bad sizes");
     for (int e = 0; e < elements; ++e)
         if (first_dof[e] != e) return fail(ADSB_EINVAL, "set_axis_tables: repeated knots are not supported");
     if (int rc = select_device(c)) return rc;
@@ -659,6 +661,7 @@ int adsb_set_axis_tables(adsb_ctx* c, int axis, int p, int elements, int q, int 
     a.w.assign(w, w + q);
     a.J.assign(J, J + elements);
     std::vector<double> ab((size_t) (3 * p + 1) * a.n), rows;
+    CU(cudaStreamSynchronize(c->stream));  // kernels in flight may still read the tables replaced below
     cudaFree(a.d_M);
     cudaFree(a.d_S);
     cudaFree(a.d_MST);
@@ -816,14 +819,16 @@ int adsb_set_plane(adsb_ctx* c, int b, int axis, int idx, const double* values) 
     if (int rc = select_device(c)) return rc;
     adsb_view v = local_view(c);
     size_t count = (size_t) c->cnt[0] * c->cnt[1] * c->cnt[2] / c->cnt[axis];
+    if (!values) return fail(ADSB_EINVAL, "set_plane: null values");
     double* d = nullptr;
     CU(cudaMalloc((void**) &d, count * sizeof(double)));
-    CU(cudaMemcpyAsync(d, values, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    cudaError_t e = (cudaError_t) launch_set_plane(c->buf[b], v.s, v.n, axis, idx, d, c->stream);
+    cudaError_t e = cudaMemcpyAsync(d, values, count * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = (cudaError_t) launch_set_plane(c->buf[b], v.s, v.n, axis, idx, d, c->stream);
     c->launches++;
-    CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
+    const cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(d);  // on every path
     if (e != cudaSuccess) return cuda_fail(e, "set_plane kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "set_plane kernel");
     return ADSB_OK;
 }
 

@@ -313,10 +313,12 @@ int sweep_strided_maps(const SweepGeom& G, int n, int NL, const long long* off_i
     if (!ptr_ok || G.s0_in != 1 || G.s0_out != 1 || (G.L1 > 1 && (!even(G.s1_in) || !even(G.s1_out)))) return -1;
     std::vector<Box> bin, bout;
     if (!cut_boxes(n, off_in_h, G.sj_in, bin) || !cut_boxes(n, off_out_h, G.sj_out, bout)) return -1;
+    // a box of several rows needs a positive, even row stride (a descending or repeating offset table cannot be
+    // one tensor map: the register-path kernel takes such sweeps)
     for (const auto& b : bin)
-        if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+        if (!even(b.off) || (b.rows > 1 && (!even(b.stride) || b.stride <= 0))) return -1;
     for (const auto& b : bout)
-        if (!even(b.off) || (b.rows > 1 && !even(b.stride))) return -1;
+        if (!even(b.off) || (b.rows > 1 && (!even(b.stride) || b.stride <= 0))) return -1;
     T.nbox_in = (int) bin.size();
     T.nbox_out = (int) bout.size();
     T.load_bytes = 0;

@@ -431,7 +431,10 @@ class SlabSim:
             for sub in self.substeps:
                 self.phase_fused(sub)
                 self.phase_finish()
-                self.peers.barrier(0)   # the neighbours' boundary planes have landed in my halo regions
+                # the neighbours' boundary planes have landed in my halo regions; consecutive barriers alternate
+                # between two signal-pad channels
+                self._bar = 1 - getattr(self, "_bar", 1) if os.environ.get("ADSB_SLAB_BARRIER_ALT", "1") != "0" else 0
+                self.peers.barrier(self._bar)
                 self._mark("barrier")
             return
         for sub in self.substeps:

@@ -82,13 +82,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ok = fused_sweep_check(rank, world, local)
+    ok = True if os.environ.get("ADSB_CHECK_CASES") else fused_sweep_check(rank, world, local)
     cases = [("heat_3d", 2, 30, 1e-7), ("heat_3d", 3, 8 * world + 5, 1e-7), ("implicit_3d", 3, 30, 1e-2),
              ("scalability_3d", 2, 30, 1e-6), ("scalability_3d", 5, 12 * world, 1e-6)]
     if world == 2:
         cases.append(("heat_3d", 2, 94, 1e-7))   # 48-plane slabs: the fused one-kernel z sweep inside whole steps
     if os.environ.get("ADSB_CHECK_QUICK"):
         cases = cases[:2]
+    if os.environ.get("ADSB_CHECK_CASES"):  # e.g. "4,5"
+        cases = [cases[int(k)] for k in os.environ["ADSB_CHECK_CASES"].split(",")]
     for problem, p, ne, dt in cases:
         n = ne + p
         u0 = synthetic_state((n, n, n))

@@ -625,3 +625,45 @@ def test_device_norms_and_errors(name, p, ne):
     tab = np.broadcast_to(np.cos(3 * x) * (y + 0.5) * (1 + z), wJ.shape).copy()
     e_tab = np.sqrt(np.sum((vals[0] - tab) ** 2 * wJ))
     assert abs(sim.ctx.norm(U, "L2", ref_values=tab)[0] - e_tab) < 1e-12 * e_tab
+
+
+# ---------------------------------------------------------------------- output sampling
+@pytest.mark.parametrize("name,p,ne,n", [("heat_2d", 3, 21, 40), ("heat_3d", 2, 11, 17), ("scalability_3d", 5, 7, 12)])
+def test_output_sampling_matches_host_spline_evaluation(name, p, ne, n, tmp_path):
+    """output_manager: the spline on a regular grid (adsb_sample) against bspline::eval restated with the host
+    entry points (find_span + basis functions + the (p+1)^d sum), then the reference's file formats"""
+    from iga_ads_b200.output import output_manager
+
+    sim = make_problem(name, p, ne, 1e-5)
+    u = synthetic_state(sim.shape())
+    sim.set_state(u)
+    om = output_manager(sim, n)
+    got = om.evaluate()
+    mats = []
+    for d, pts in zip(sim.dims, om.points):
+        E = np.zeros((len(pts), d.dofs()))
+        for i, x in enumerate(pts):
+            span = ads.find_span(x, d.knot, d.p)
+            E[i, span - d.p:span + 1] = ads.basis_ders(span, x, d.knot, d.p, 0)[0]
+        mats.append(E)
+    if len(mats) == 2:
+        U2 = u.reshape(sim.dims[1].dofs(), sim.dims[0].dofs())
+        want = mats[0] @ U2.T @ mats[1].T                                 # [i, j]
+    else:
+        U3 = u.reshape(sim.dims[2].dofs(), sim.dims[1].dofs(), sim.dims[0].dofs())
+        want = np.einsum("ia,jb,kc,cba->ijk", mats[0], mats[1], mats[2], U3, optimize=True)
+    assert got.shape == want.shape == (n + 1,) * len(mats)
+    assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
+    path = tmp_path / "out.data"
+    om.to_file(str(path))
+    text = path.read_text().splitlines()
+    if len(mats) == 3:
+        assert text[1] == '<VTKFile type="ImageData" version="0.1">' and text[-1] == "</VTKFile>"
+        assert f'WholeExtent="0 {n} 0 {n} 0 {n}"' in text[2]
+        body = np.array([float(v) for v in text[6:6 + (n + 1) ** 3]])
+        assert np.abs(body - got.ravel(order="F")).max() < 1e-10 and len(text[6]) == 18
+    else:
+        rows = np.array([[float(v) for v in ln.split()] for ln in text])
+        assert rows.shape == ((n + 1) ** 2, 3) and len(text[0]) == 54
+        assert np.abs(rows[:, 2] - got.ravel()).max() < 1e-10
+        assert np.allclose(rows[: n + 1, 0], om.points[0][0]) and np.allclose(rows[: n + 1, 1], om.points[1])

@@ -211,3 +211,27 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(ads.AdsbError):
         sim = ads.heat_3d(2, 4, ads.timesteps_config(1, 1e-7))
         sim.prepare_matrices()
+
+
+def test_output_writers_follow_the_reference_formats():
+    """include/ads/output/vtk.hpp:45-82 and gnuplot.hpp:45-56 with DEFAULT_FMT = fixed, precision 10, width 18"""
+    import io
+
+    from iga_ads_b200.output import linspace, write_gnuplot_2d, write_vtk
+
+    assert np.array_equal(linspace(0.0, 1.0, 4), [0.0, 0.25, 0.5, 0.75, 1.0])
+    vals = np.arange(24, dtype=float).reshape((2, 3, 4), order="F") / 7
+    s = io.StringIO()
+    write_vtk(s, vals)
+    lines = s.getvalue().splitlines()
+    assert lines[0] == '<?xml version="1.0"?>'
+    assert lines[2] == '  <ImageData WholeExtent="0 1 0 2 0 3" origin="0 0 0" spacing="1 1 1">'
+    assert lines[3] == '    <Piece Extent="0 1 0 2 0 3">'
+    assert lines[5] == '        <DataArray Name="Result"  type="Float32" format="ascii" NumberOfComponents="1">'
+    assert lines[6] == "      0.0000000000" and lines[7] == "      0.1428571429"   # memory order, first index fastest
+    assert lines[6 + 24:] == ["        </DataArray>", "      </PointData>", "    </Piece>", "  </ImageData>", "</VTKFile>"]
+    s = io.StringIO()
+    write_gnuplot_2d(s, [0.0, 0.5], [0.0, 1.0, 2.0], np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]))
+    rows = s.getvalue().splitlines()
+    assert rows[1] == "      0.0000000000      1.0000000000      2.0000000000"
+    assert rows[3] == "      0.5000000000      0.0000000000      4.0000000000" and len(rows) == 6
