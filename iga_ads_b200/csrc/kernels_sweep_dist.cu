@@ -43,7 +43,8 @@ constexpr int DIST_NBUF_A = 3; // at most this many slots in the pass-A ring (G.
 
 // Boundary values validate themselves: a word of the inbox holds the sentinel until the neighbour's store has
 // replaced it.  peek() reads it (possibly still the sentinel), take() spins until the value is there and puts the
-// sentinel back; it gives up after ~2 s (sets *err; the result is then garbage but nothing hangs).
+// sentinel back; it gives up after ~30 s (sets *err; the result is then garbage but nothing hangs) -- long enough
+// for a neighbour whose host thread is late with its launch, short enough to end a run whose peer has died.
 __device__ __forceinline__ unsigned long long peek_value(const double* slot) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
@@ -57,7 +58,7 @@ __device__ __forceinline__ double take_value(double* slot, unsigned long long v,
             __nanosleep(ns);
             if (ns < 512) ns *= 2;
             v = peek_value(slot);
-            if (clock64() - t0 > 4000000000ll) {
+            if (clock64() - t0 > 60000000000ll) {
                 if (err) atomicExch(err, 1);
                 break;
             }

@@ -313,7 +313,7 @@ typedef struct {
     double* x_local;
     double* dseg_next;               /* state array of rank + 1 (peer pointer; ignored on the last rank) */
     double* x_prev;                  /* state array of rank - 1 (ignored on the first rank) */
-    int* error_flag;                 /* device int, set to 1 when a poll timed out (~2 s); may be NULL */
+    int* error_flag;                 /* device int, set to 1 when a poll timed out (~30 s); may be NULL */
     /* optional halo publishing (the right-hand side of the next step needs p planes of each neighbour): the
      * first halo_planes planes of the finished slab are also stored at halo_prev, the last ones at halo_next
      * (peer pointers into the neighbours' state buffers, same plane layout as `data`; NULL: skip) */
