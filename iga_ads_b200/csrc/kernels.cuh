@@ -107,6 +107,8 @@ struct SweepTileGeom {
 int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
                       const long long* off_out_h, cudaStream_t st);
 
+// nseg segments of the same lines in one launch (kernels_sweep_tile.cu); same return convention
+int launch_sweep_tile_multi(int nseg, const SweepFactor* Fs, const SweepGeom* Gs, bool contig, cudaStream_t st);
 int sweep_strided_maps(const SweepGeom& G, int n, int NL, const long long* off_in_h, const long long* off_out_h,
                        cudaStream_t st, SweepTileGeom& T);
 

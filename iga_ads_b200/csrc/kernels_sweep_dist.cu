@@ -58,7 +58,8 @@ __device__ __forceinline__ double take_value(double* slot, unsigned long long v,
             __nanosleep(ns);
             if (ns < 512) ns *= 2;
             v = peek_value(slot);
-            if (clock64() - t0 > 60000000000ll) {
+            // one time-out ends all waiting of this launch (and of the following ones until the caller clears *err)
+            if (clock64() - t0 > 60000000000ll || (err && *reinterpret_cast<volatile int*>(err))) {
                 if (err) atomicExch(err, 1);
                 break;
             }

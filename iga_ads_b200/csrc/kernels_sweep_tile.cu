@@ -31,8 +31,7 @@ constexpr int MAX_NBUF = 3;
 
 // Block = ncons consumer threads (NLt lanes x chunks, padded to whole warps) + one producer warp.
 template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
-__global__ void __launch_bounds__(288, 1)
-    sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G) {
+__device__ __forceinline__ void sweep_tile_body(const SweepFactor& F0, const SweepTileGeom& G) {
     constexpr int RL = SWEEP_RL, NLt = NL / RL;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int SC = F0.SC;
@@ -205,7 +204,48 @@ __global__ void __launch_bounds__(288, 1)
     }
 }
 
+template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
+__global__ void __launch_bounds__(288, 1) sweep_tile_kernel(const SweepFactor F0, const SweepTileGeom G) {
+    sweep_tile_body<KL, KD, PIV, CH, NL, CONTIG>(F0, G);
+}
+
+// Several segments of the same lines in ONE launch (lines too long for one CTA, api.cu: sweep_segmented): the
+// CTAs with blockIdx.y = s work on segment s -- its own factor and its own tile geometry, read once from
+// global memory into shared memory.
+struct SweepSegArgs {
+    SweepFactor F;
+    SweepTileGeom G;
+};
+template <int KL, int KD, bool PIV, int CH, int NL, bool CONTIG>
+__global__ void __launch_bounds__(288, 1) sweep_tile_multi_kernel(const SweepSegArgs* __restrict__ segs) {
+    __shared__ SweepSegArgs a;
+    static_assert(sizeof(SweepSegArgs) % 4 == 0, "copied word by word");
+    const int* src = reinterpret_cast<const int*>(segs + blockIdx.y);
+    int* dst = reinterpret_cast<int*>(&a);
+    for (int i = threadIdx.x; i < (int) (sizeof(SweepSegArgs) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    sweep_tile_body<KL, KD, PIV, CH, NL, CONTIG>(a.F, a.G);
+}
+
 using tile_kern_t = void (*)(const SweepFactor, const SweepTileGeom);
+using tile_multi_kern_t = void (*)(const SweepSegArgs*);
+
+template <int P, bool PIV>
+tile_multi_kern_t pick_multi_mode(bool contig) {  // long lines: always 16 lines per tile
+    constexpr int KD = PIV ? 2 * P : P;
+    return contig ? (tile_multi_kern_t) sweep_tile_multi_kernel<P, KD, PIV, SWEEP_CH, 16, true>
+                  : (tile_multi_kern_t) sweep_tile_multi_kernel<P, KD, PIV, SWEEP_CH, 16, false>;
+}
+tile_multi_kern_t pick_multi(int KL, bool piv, bool contig) {
+    switch (KL) {
+    case 1: return piv ? pick_multi_mode<1, true>(contig) : pick_multi_mode<1, false>(contig);
+    case 2: return piv ? pick_multi_mode<2, true>(contig) : pick_multi_mode<2, false>(contig);
+    case 3: return piv ? pick_multi_mode<3, true>(contig) : pick_multi_mode<3, false>(contig);
+    case 4: return piv ? pick_multi_mode<4, true>(contig) : pick_multi_mode<4, false>(contig);
+    case 5: return piv ? pick_multi_mode<5, true>(contig) : pick_multi_mode<5, false>(contig);
+    default: return nullptr;
+    }
+}
 
 template <int P, bool PIV, int NL>
 tile_kern_t pick_mode(bool contig) {
@@ -353,10 +393,17 @@ int sweep_strided_maps(const SweepGeom& G, int n, int NL, const long long* off_i
     return 0;
 }
 
-// Returns cudaSuccess (0) when the tile kernel was launched, -1 when this sweep is not eligible (the
-// caller then uses the register-path kernel), or a CUDA error.
-int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
-                      const long long* off_out_h, cudaStream_t st) {
+namespace {
+
+struct TilePrep {
+    SweepTileGeom T{};
+    size_t smem = 0;
+    int NL = 0, ncons = 0;
+};
+
+// Geometry, tensor maps and shared-memory budget of one tile sweep.  0: ready; -1: not eligible; else cudaError_t.
+int prepare_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
+                       const long long* off_out_h, cudaStream_t st, int force_NL, TilePrep& P) {
     // lines per tile: as many lanes as keep the CTA near 256 consumer threads (lanes x chunks): 16 lines for
     // 17..32 chunks (n <= 576), 32 for 9..16, 64 for 5..8, 128 for <= 4 chunks (the thin slabs of a sharded z
     // sweep); wider tiles also move longer rows (128 B .. 1 KB).  ADSB_SWEEP_NL=12|16|32|64|128 pins it.
@@ -365,14 +412,11 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
         const int v = e ? atoi(e) : 0;
         return (v == 12 || v == 16 || v == 32 || v == 64 || v == 128) ? v : 0;
     }();
-    int NL = NL_env;
+    int NL = force_NL ? force_NL : NL_env;
     if (!NL) {
         // shared memory of a CTA with nl lines per tile and two ring slots (same arithmetic as below)
         auto fits = [&](int nl) {
-            const size_t rows = (size_t) F.SC * SWEEP_CH + F.KL + F.KD;
-            const size_t fixed = ((size_t) F.SC * (F.KL + F.KD) * nl +
-                                  rows * (sweep_pitch(F.KL) + sweep_pitch(F.KD + 1) + sweep_pitch(F.KD + F.KL)) +
-                                  (size_t) F.SC * (F.KL * F.KL + F.KD * F.KD) * SWEEP_MAX_DEPTH_DEV) * 8 + 256;
+            const size_t fixed = ((size_t) F.SC * (F.KL + F.KD) * nl + (size_t) F.blob_doubles) * 8 + 256;
             const size_t tile = ((size_t) F.SC * SWEEP_CH + F.KL + 18) * nl * 8;
             return fixed + 2 * tile <= 226 * 1024;
         };
@@ -387,7 +431,8 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
     if (contig && SWEEP_CH % 2) return -1;  // the 128-bit chunk path needs an even CH
     auto even = [](long long v) { return (v & 1) == 0; };
     const bool ptr_ok = ((uintptr_t) G.in % 16 == 0) && ((uintptr_t) G.out % 16 == 0);
-    SweepTileGeom T{};
+    SweepTileGeom& T = P.T;
+    T = SweepTileGeom{};
     T.in = G.in;
     T.out = G.out;
     T.L0 = G.L0;
@@ -420,24 +465,92 @@ int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, con
     int nbuf = (int) ((budget - fixed_bytes) / ((size_t) T.tile_doubles * 8));
     if (nbuf > MAX_NBUF) nbuf = MAX_NBUF;
     T.nbuf = nbuf;
-    const size_t smem = (size_t) nbuf * T.tile_doubles * 8 + fixed_bytes;
-    tile_kern_t k = NL == 12 ? pick<12>(F.KL, F.piv != 0, contig)
-                    : NL == 32 ? pick<32>(F.KL, F.piv != 0, contig)
-                    : NL == 64 ? pick<64>(F.KL, F.piv != 0, contig)
-                    : NL == 128 ? pick<128>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
-    if (!k) return -1;
-    cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return (int) e;
+    P.smem = (size_t) nbuf * T.tile_doubles * 8 + fixed_bytes;
+    P.NL = NL;
+    P.ncons = ncons;
+    return 0;
+}
+
+int device_sm_count() {
     static int sms = [] {
         int dev = 0, v = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         return v;
     }();
-    dim3 block(ncons + 32, 1, 1);
+    return sms;
+}
+
+std::map<std::vector<long long>, void*> g_multi_cache;  // SweepSegArgs arrays already resident on the device
+
+}  // namespace
+
+// Returns cudaSuccess (0) when the tile kernel was launched, -1 when this sweep is not eligible (the
+// caller then uses the register-path kernel), or a CUDA error.
+int launch_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, const long long* off_in_h,
+                      const long long* off_out_h, cudaStream_t st) {
+    TilePrep P;
+    if (int rc = prepare_sweep_tile(F, G, contig, off_in_h, off_out_h, st, 0, P)) return rc;
+    const int NL = P.NL;
+    tile_kern_t k = NL == 12 ? pick<12>(F.KL, F.piv != 0, contig)
+                    : NL == 32 ? pick<32>(F.KL, F.piv != 0, contig)
+                    : NL == 64 ? pick<64>(F.KL, F.piv != 0, contig)
+                    : NL == 128 ? pick<128>(F.KL, F.piv != 0, contig) : pick<16>(F.KL, F.piv != 0, contig);
+    if (!k) return -1;
+    cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P.smem);
+    if (e != cudaSuccess) return (int) e;
+    const int sms = device_sm_count();
+    dim3 block(P.ncons + 32, 1, 1);
     const int cap = (G.max_ctas > 0 && G.max_ctas < sms) ? G.max_ctas : sms;
-    dim3 grid(T.ntiles < cap ? T.ntiles : cap, 1, 1);
-    return (int) launch_ex(k, grid, block, smem, st, true, F, T);
+    dim3 grid(P.T.ntiles < cap ? P.T.ntiles : cap, 1, 1);
+    return (int) launch_ex(k, grid, block, P.smem, st, true, F, P.T);
+}
+
+// nseg segments of the same lines (Fs[s] on the rows Gs[s] addresses) in one launch, the SMs shared out evenly.
+// 0: launched; -1: not eligible (the caller launches segment by segment); else cudaError_t.
+int launch_sweep_tile_multi(int nseg, const SweepFactor* Fs, const SweepGeom* Gs, bool contig, cudaStream_t st) {
+    if (nseg < 1) return -1;
+    std::vector<SweepSegArgs> args(nseg);
+    size_t smem = 0;
+    int ncons = 0, ntiles = 0;
+    for (int s = 0; s < nseg; ++s) {
+        TilePrep P;
+        if (int rc = prepare_sweep_tile(Fs[s], Gs[s], contig, nullptr, nullptr, st, 16, P)) return rc;
+        if (Fs[s].KL != Fs[0].KL || Fs[s].KD != Fs[0].KD || Fs[s].piv != Fs[0].piv) return -1;  // one kernel variant
+        args[s].F = Fs[s];
+        args[s].G = P.T;
+        smem = std::max(smem, P.smem);
+        ncons = std::max(ncons, P.ncons);
+        ntiles = std::max(ntiles, P.T.ntiles);
+    }
+    tile_multi_kern_t k = pick_multi(Fs[0].KL, Fs[0].piv != 0, contig);
+    if (!k) return -1;
+    // the argument array lives on the device; one per distinct set of operands (a time loop alternates two)
+    std::vector<long long> key;
+    for (int s = 0; s < nseg; ++s)
+        key.insert(key.end(), {(long long) (uintptr_t) Gs[s].in, (long long) (uintptr_t) Gs[s].out, (long long) (uintptr_t) Fs[s].cfF,
+                               (long long) (uintptr_t) args[s].G.maps, Gs[s].L0, Gs[s].L1, Gs[s].s0_in, Gs[s].s1_in, Gs[s].s0_out,
+                               Gs[s].s1_out, Gs[s].sj_in, Gs[s].sj_out, (long long) contig});
+    void* d_args = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        auto it = g_multi_cache.find(key);
+        if (it == g_multi_cache.end()) {
+            if (cudaMalloc(&d_args, args.size() * sizeof(SweepSegArgs)) != cudaSuccess) return -1;
+            cudaError_t e = cudaMemcpyAsync(d_args, args.data(), args.size() * sizeof(SweepSegArgs), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `args` is a local
+            if (e != cudaSuccess) return (int) e;
+            it = g_multi_cache.emplace(std::move(key), d_args).first;
+        }
+        d_args = it->second;
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void*) k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    const int sms = device_sm_count();
+    const int cap = (Gs[0].max_ctas > 0 && Gs[0].max_ctas < sms) ? Gs[0].max_ctas : sms;
+    const int per = std::max(1, std::min(ntiles, cap / nseg));
+    dim3 block(ncons + 32, 1, 1), grid(per, nseg, 1);
+    return (int) launch_ex(k, grid, block, smem, st, true, (const SweepSegArgs*) d_args);
 }
 
 }  // namespace adsb
