@@ -128,6 +128,7 @@ _SIGNATURES = {
     "adsb_seg_sweep_view": (c_int, [vp, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp, ctypes.POINTER(View)]),
     "adsb_dist_sweep_view": (c_int, [vp, c_int, c_int, vp, ctypes.POINTER(View), ctypes.POINTER(DistArgs)]),
     "adsb_dist_sweep_check": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(View), c_int, c_int]),
+    "adsb_neighbor_barrier": (c_int, [vp, vp, vp, vp, vp]),
     "adsb_seg_dseg_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View),
                                    ctypes.POINTER(vp), c_int]),
     "adsb_seg_din_view": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, ctypes.POINTER(View), vp, vp,

@@ -1191,30 +1191,69 @@ int sweep_segmented(adsb_ctx* c, int axis, int slot, const double* in, const ads
     }
     StageTimer t(c, 1 + axis);
     cudaStream_t main_stream = c->stream;
+    // pass A, preferably ONE launch: the CTAs with blockIdx.y = s sweep segment s (csrc/kernels_sweep_tile.cu)
+    bool launched = false;
+    {
+        const int ax1 = (axis + 1) % 3, ax2 = (axis + 2) % 3;
+        const bool contig = vi.s[axis] == 1 && vo.s[axis] == 1;
+        int l0 = (vi.s[ax1] <= vi.s[ax2]) ? ax1 : ax2;
+        if (!contig && vi.n[l0] == 1) l0 = (l0 == ax1) ? ax2 : ax1;
+        const int l1 = (l0 == ax1) ? ax2 : ax1;
+        std::vector<SweepGeom> Gs(S);
+        for (int s = 0; s < S; ++s) {
+            const int a0 = g.bounds[s];
+            SweepGeom& Q = Gs[s];
+            Q = SweepGeom{};
+            Q.in = in + (long long) a0 * vi.s[axis];
+            Q.out = out + (long long) a0 * vo.s[axis];
+            Q.sj_in = vi.s[axis];
+            Q.sj_out = vo.s[axis];
+            Q.L0 = vi.n[l0];
+            Q.L1 = vi.n[l1];
+            Q.s0_in = vi.s[l0];
+            Q.s0_out = vo.s[l0];
+            Q.s1_in = vi.s[l1];
+            Q.s1_out = vo.s[l1];
+            Q.max_ctas = c->sm_limit;
+            if (!contig) flatten_lines(Q);
+            Q.pad_ok = managed && in == out && axis == 0 && vi.s[1] > vi.n[0] && s == S - 1;  // only the last segment ends at the pad
+        }
+        static const bool multi_on = [] {
+            const char* e = getenv("ADSB_SEG_ONE_LAUNCH");
+            return !e || atoi(e) != 0;
+        }();
+        const int rcm = multi_on ? launch_sweep_tile_multi(S, g.local.data(), Gs.data(), contig, main_stream) : -1;
+        if (rcm > 0) return cuda_fail((cudaError_t) rcm, "segmented sweep (one launch)");
+        launched = rcm == 0;
+        if (launched) c->launches++;
+    }
     const int keep_limit = c->sm_limit;
     const bool keep_timing = c->timing;
-    const int sms = (keep_limit > 0 && keep_limit < device_sms()) ? keep_limit : device_sms();
-    CU(cudaEventRecord(c->seg_events[0], main_stream));
     int rc = ADSB_OK;
-    c->timing = false;
-    c->sm_limit = std::max(1, sms / ns);
-    for (int s = 0; s < S && rc == ADSB_OK; ++s) {
-        cudaStream_t st = c->seg_streams[s % ns];
-        if (s < ns) CU(cudaStreamWaitEvent(st, c->seg_events[0], 0));
-        const int a = g.bounds[s], rows = g.bounds[s + 1] - a;
-        adsb_view svi = vi, svo = vo;
-        svi.n[axis] = svo.n[axis] = rows;
-        c->stream = st;
-        rc = sweep_impl(c, axis, slot, in + (long long) a * vi.s[axis], svi, nullptr, out + (long long) a * vo.s[axis], svo,
-                        nullptr, managed, &g.local[s]);
-    }
-    c->stream = main_stream;
-    c->sm_limit = keep_limit;
-    c->timing = keep_timing;
-    if (rc != ADSB_OK) return rc;
-    for (int i = 0; i < ns; ++i) {
-        CU(cudaEventRecord(c->seg_events[1 + i], c->seg_streams[i]));
-        CU(cudaStreamWaitEvent(main_stream, c->seg_events[1 + i], 0));
+    if (!launched) {
+        // fall-back: one launch per segment, side by side on a few streams
+        const int sms = (keep_limit > 0 && keep_limit < device_sms()) ? keep_limit : device_sms();
+        CU(cudaEventRecord(c->seg_events[0], main_stream));
+        c->timing = false;
+        c->sm_limit = std::max(1, sms / ns);
+        for (int s = 0; s < S && rc == ADSB_OK; ++s) {
+            cudaStream_t st = c->seg_streams[s % ns];
+            if (s < ns) CU(cudaStreamWaitEvent(st, c->seg_events[0], 0));
+            const int a = g.bounds[s], rows = g.bounds[s + 1] - a;
+            adsb_view svi = vi, svo = vo;
+            svi.n[axis] = svo.n[axis] = rows;
+            c->stream = st;
+            rc = sweep_impl(c, axis, slot, in + (long long) a * vi.s[axis], svi, nullptr, out + (long long) a * vo.s[axis], svo,
+                            nullptr, managed, &g.local[s]);
+        }
+        c->stream = main_stream;
+        c->sm_limit = keep_limit;
+        c->timing = keep_timing;
+        if (rc != ADSB_OK) return rc;
+        for (int i = 0; i < ns; ++i) {
+            CU(cudaEventRecord(c->seg_events[1 + i], c->seg_streams[i]));
+            CU(cudaStreamWaitEvent(main_stream, c->seg_events[1 + i], 0));
+        }
     }
     double* dst1[1] = {dseg};
     double* dst2[1] = {xst};
@@ -1349,6 +1388,16 @@ int adsb_dist_sweep_view(adsb_ctx* c, int axis, int slot, double* data, const ad
     if (rc == -1) rc = launch_sweep_dist(F, SWEEP_CH, g->dev, G, D, d->nl, c->stream);
     if (rc == -1) return fail(ADSB_ESTATE, "dist_sweep_view: this factor / view is not eligible for the fused kernel");
     if (rc != 0) return cuda_fail((cudaError_t) rc, "distributed sweep kernel launch");
+    c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_neighbor_barrier(adsb_ctx* c, unsigned long long* flags_local, unsigned long long* flags_prev,
+                          unsigned long long* flags_next, int* error_flag) {
+    if (!c || !flags_local) return fail(ADSB_EINVAL, "neighbor_barrier: null argument");
+    if (int rc = select_device(c)) return rc;
+    cudaError_t e = (cudaError_t) launch_neighbor_barrier(flags_local, flags_prev, flags_next, error_flag, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "neighbour barrier kernel");
     c->launches++;
     return ADSB_OK;
 }

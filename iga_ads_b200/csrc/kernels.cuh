@@ -224,6 +224,8 @@ struct SweepDistArgs {
     double* halo_next;
     int halo_planes;
 };
+int launch_neighbor_barrier(unsigned long long* mine, unsigned long long* prev, unsigned long long* next, int* err,
+                            cudaStream_t st);
 // dry_run: only report eligibility (0 / -1), launch nothing
 int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,
                       cudaStream_t st, bool dry_run = false);

@@ -433,6 +433,31 @@ __global__ void __launch_bounds__(384, 1)
     }
 }
 
+// Barrier with the two neighbouring ranks only (every dependency of the slab-sharded step is between
+// neighbours): bump a device-side counter, publish it to the neighbours' flag words, wait for theirs.
+// flags (symmetric memory, zero-initialised): [0] written by the previous rank, [1] by the next, [2] own counter.
+__global__ void neighbor_barrier_kernel(unsigned long long* mine, unsigned long long* prev, unsigned long long* next,
+                                        int* err) {
+    if (threadIdx.x != 0) return;
+    const unsigned long long c = mine[2] + 1;
+    mine[2] = c;
+    __threadfence_system();
+    if (prev) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(prev + 1), "l"(c) : "memory");
+    if (next) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(next), "l"(c) : "memory");
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+        if (!(side == 0 ? prev : next)) continue;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + side) : "memory");
+            if (clock64() - t0 > 60000000000ll) {
+                if (err) atomicExch(err, 1);
+                return;
+            }
+        } while (v < c);
+    }
+}
+
 using dist_kern_t = void (*)(const SweepFactor, const SegDev, const SweepTileGeom, const SweepDistArgs);
 
 template <int P, bool PIV, int CH>
@@ -466,6 +491,12 @@ dist_kern_t pick(int KL, bool piv, int NL, int CH) {
 }
 
 }  // namespace
+
+int launch_neighbor_barrier(unsigned long long* mine, unsigned long long* prev, unsigned long long* next, int* err,
+                            cudaStream_t st) {
+    neighbor_barrier_kernel<<<1, 32, 0, st>>>(mine, prev, next, err);
+    return (int) cudaGetLastError();
+}
 
 // 0: launched; -1: not eligible (the caller runs pass A / boundary kernels / pass B separately); else cudaError_t
 int launch_sweep_dist(const SweepFactor& F, int CH, const SegDev& T, const SweepGeom& G, const SweepDistArgs& D, int NL,

@@ -177,6 +177,12 @@ class Context:
         check(self.lib.adsb_seg_sweep_view(self.h, axis, slot, seg, ctypes.c_void_p(in_ptr), ctypes.byref(vin),
                                            ctypes.c_void_p(out_ptr), ctypes.byref(vout)))
 
+    def neighbor_barrier(self, flags_local, flags_prev, flags_next, error_flag=None):
+        """barrier with the two neighbouring ranks on this context's stream (device pointers; None at the ends)"""
+        vp = ctypes.c_void_p
+        check(self.lib.adsb_neighbor_barrier(self.h, vp(flags_local), vp(flags_prev) if flags_prev else None,
+                                             vp(flags_next) if flags_next else None, vp(error_flag) if error_flag else None))
+
     def dist_sweep_check(self, axis, slot, rank, view, nl, lag):
         return check(self.lib.adsb_dist_sweep_check(self.h, axis, slot, rank, ctypes.byref(view), nl, lag)) == 1
 

@@ -173,7 +173,8 @@ class SlabSim:
         f64 = dict(dtype=torch.float64, device=self.dev)
         S = world
         nhalo = (max(np.diff(self.bounds)) + 2 * p) * self.plane
-        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines)]
+        sizes = [("h0", int(nhalo)), ("h1", int(nhalo)), ("dseg", S * KL * self.lines), ("x", S * KD * self.lines),
+                 ("nbflags", 4)]   # neighbour barrier: 64-bit words [from prev, from next, own counter, -]
         if peers is None and world > 1:
             peers = _SymmPeers(self, sizes)
             self.sym = {name: peers.local(name) for name, _ in sizes}
@@ -203,6 +204,7 @@ class SlabSim:
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.fused = False
         self.halo_in_kernel = os.environ.get("ADSB_SLAB_HALO_IN_KERNEL", "1") != "0"   # fused sweep stores the halos itself
+        self.neighbor_barrier = os.environ.get("ADSB_SLAB_NEIGHBOR_BARRIER", "1") != "0"
         self.want_fused = world > 1 and os.environ.get("ADSB_SLAB_FUSED", "1") != "0"
         self.cur = 0
         self.launches = 0
@@ -433,8 +435,7 @@ class SlabSim:
                 self.phase_finish()
                 # the neighbours' boundary planes have landed in my halo regions; consecutive barriers alternate
                 # between two signal-pad channels
-                self._bar = 1 - getattr(self, "_bar", 1) if os.environ.get("ADSB_SLAB_BARRIER_ALT", "1") != "0" else 0
-                self.peers.barrier(self._bar)
+                self.step_barrier()
                 self._mark("barrier")
             return
         for sub in self.substeps:
@@ -447,6 +448,17 @@ class SlabSim:
             self.phase_correct(sub)
             self.peers.barrier(2)
             self._mark("barrier")
+
+    def step_barrier(self):
+        """end of a fused sub-step: the neighbours' halo stores have landed and they are done with my boundary values.
+        Everything is between neighbours, so a two-neighbour flag barrier replaces the all-rank signal barrier."""
+        if self.neighbor_barrier and isinstance(self.peers, _SymmPeers):
+            r, S = self.rank, self.world
+            self.ctx.neighbor_barrier(self.sym["nbflags"].data_ptr(), self.peers.ptr(r - 1, "nbflags") if r > 0 else None,
+                                      self.peers.ptr(r + 1, "nbflags") if r + 1 < S else None, self.err_flag.data_ptr())
+        else:
+            self._bar = 1 - getattr(self, "_bar", 1)
+            self.peers.barrier(self._bar)
 
     def advance(self, nsteps, graph=None):
         """nsteps steps; with graph=True (default on > 1 GPU, ADSB_SLAB_GRAPH=0 disables) one step is captured

@@ -328,6 +328,14 @@ int adsb_dist_sweep_view(adsb_ctx* ctx, int axis, int slot, double* data, const 
  * lets every rank of a run agree on the path before anything is launched. */
 int adsb_dist_sweep_check(adsb_ctx* ctx, int axis, int slot, int rank, const adsb_view* view, int nl, int lag);
 
+/* Barrier with the two neighbouring ranks on the context's stream (a one-thread kernel): every dependency of
+ * the slab-sharded step -- halo planes, re-use of the boundary-value arrays -- is between neighbours, so the
+ * ranks need no all-to-all barrier.  flags_*: 3 64-bit words per rank in peer-mapped, zero-initialised memory
+ * ([0] written by the previous rank, [1] by the next, [2] the rank's own counter, which makes the call safe
+ * to replay from a CUDA graph); flags_prev / flags_next are the neighbours' arrays (NULL at the ends). */
+int adsb_neighbor_barrier(adsb_ctx* ctx, unsigned long long* flags_local, unsigned long long* flags_prev,
+                          unsigned long long* flags_next, int* error_flag);
+
 int adsb_seg_dseg_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
                        const adsb_view* vin, double* const* dst, int ndst);
 int adsb_seg_din_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* xhat,
