@@ -480,15 +480,26 @@ class SlabSim:
                 n -= 1
 
     def _capture(self):
+        import gc
+
         torch = self.torch
         main = torch.cuda.current_stream(self.dev)
         l0, b0 = self.launches, self.exchange_bytes
+        # no allocation may be freed while the stream is capturing: collect garbage now (an earlier simulation's
+        # symmetric memory, say) and keep the collector off until the capture has ended
+        gc.collect()
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
-            self.step()
-            self.step()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g):
+                self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+                self.step()
+                self.step()
+        finally:
+            if gc_was_on:
+                gc.enable()
         self.ctx.set_stream(main.cuda_stream)
         self._graph_delta = (self.launches - l0, self.exchange_bytes - b0)
         self.launches, self.exchange_bytes = l0, b0

@@ -124,6 +124,11 @@ def main():
             ok = ok and sim.graph is not None and err < 6 * (1e-12 if p <= 3 else 1e-10)
         ok = ok and int(sim.err_flag.item()) == 0   # no boundary-value poll timed out
         del sim
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
