@@ -357,6 +357,14 @@ int sweep_impl(adsb_ctx* c, int axis, int slot, const double* in, const adsb_vie
     G.s1_in = vi.s[l1];
     G.s1_out = vo.s[l1];
     G.max_ctas = c->sm_limit;
+    // The x sweep follows the right-hand side, which writes its planes in ascending z: walking the x tiles from
+    // the last plane backwards starts on what is still in L2 (it matters when a tensor is not much larger than
+    // the 126 MB L2: 256^3 problems, the slabs of an 8-GPU run); the y sweep then walks forwards again.
+    static const bool reverse_x = [] {
+        const char* e = getenv("ADSB_SWEEP_REVERSE_X");
+        return !e || atoi(e) != 0;
+    }();
+    G.reverse = (reverse_x && axis == 0 && c->ndim == 3) ? 1 : 0;
     if (!contig && !off_in && !off_out) flatten_lines(G);
     // managed tensors pad every x row: an in-place x sweep of an odd-length line may move the pad along
     G.pad_ok = managed && in == out && axis == 0 && vi.s[1] > vi.n[0];

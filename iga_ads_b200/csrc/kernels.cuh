@@ -78,6 +78,7 @@ struct SweepGeom {
     int pitch;  // CONTIG: shared-memory row pitch in doubles (even)
     int bulk;   // CONTIG: rows are 16 B aligned on both sides -> TMA bulk copies
     int max_ctas;  // persistent kernels: at most this many CTAs (0: one per SM)
+    int reverse;   // tile kernel: walk the tiles from the last one backwards (start on what the previous kernel left in L2)
     int pad_ok;    // CONTIG, odd n: every line is followed by a pad element inside the allocation (managed
                    // tensors, in place): bulk copies may move n+1 doubles so that they stay 16 B multiples
 };
@@ -100,6 +101,7 @@ struct SweepTileGeom {
     int tile_doubles;  // shared-memory doubles per ring slot
     int nbuf;          // ring depth
     long long s_row;   // element stride of the rows (fused distributed sweep: halo stores address planes directly)
+    int reverse;       // tiles in descending order
 };
 // 0: launched; -1: not eligible (caller falls back to launch_sweep); otherwise a cudaError_t.
 // off_in_h / off_out_h: optional host row-offset tables (see adsb_sweep_view); they must be piecewise

@@ -87,7 +87,7 @@ __device__ __forceinline__ void sweep_tile_body(const SweepFactor& F0, const Swe
         bulk_g2s(s_tab, F0.cfF, (uint32_t) (F0.blob_doubles * 8), tabbar);
         pdl_wait();  // the tensor itself: only once the previous kernel of the stream has finished with it
         auto issue_load = [&](int i) {
-            const int t = blockIdx.x + i * gridDim.x;
+            const int t = G.reverse ? G.ntiles - 1 - ((int) blockIdx.x + i * (int) gridDim.x) : (int) blockIdx.x + i * (int) gridDim.x;
             const int bx = t % G.nb0, m = t / G.nb0;
             const int b = i % G.nbuf;
             double* dst = tiles + (size_t) b * tile_doubles;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void sweep_tile_body(const SweepFactor& F0, const Swe
             }
         };
         auto issue_store = [&](int i) {
-            const int t = blockIdx.x + i * gridDim.x;
+            const int t = G.reverse ? G.ntiles - 1 - ((int) blockIdx.x + i * (int) gridDim.x) : (int) blockIdx.x + i * (int) gridDim.x;
             const int bx = t % G.nb0, m = t / G.nb0;
             const int b = i % G.nbuf;
             const double* src = tiles + (size_t) b * tile_doubles;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void sweep_tile_body(const SweepFactor& F0, const Swe
         double v[RL][CH + KL];
         bool act[RL];
         if (CONTIG) {
-            const int t = blockIdx.x + i * gridDim.x;
+            const int t = G.reverse ? G.ntiles - 1 - ((int) blockIdx.x + i * (int) gridDim.x) : (int) blockIdx.x + i * (int) gridDim.x;
             const int lbase = (t % G.nb0) * NL;
 #pragma unroll
             for (int r = 0; r < RL; ++r) {
@@ -443,6 +443,7 @@ int prepare_sweep_tile(const SweepFactor& F, const SweepGeom& G, bool contig, co
     T.s1_out = G.s1_out;
     T.nb0 = (G.L0 + NL - 1) / NL;
     T.ntiles = T.nb0 * G.L1;
+    T.reverse = G.reverse;
     const int rows_needed = F.SC * SWEEP_CH + F.KL;
     if (contig) {
         if (!ptr_ok || !even(G.s0_in) || !even(G.s1_in) || !even(G.s0_out) || !even(G.s1_out)) return -1;
