@@ -115,6 +115,7 @@ _SIGNATURES = {
     "adsb_project_init": (c_int, [vp, c_int, c_int]),
     "adsb_sample": (c_int, [vp, c_int, ip, ctypes.POINTER(dp), ctypes.POINTER(dp), dp]),
     "adsb_norm": (c_int, [vp, c_int, c_int, c_int, c_dbl, dp, dp]),
+    "adsb_project_values": (c_int, [vp, c_int, c_int, c_int, dp, c_int]),
     "adsb_solve": (c_int, [vp, c_int, ip]),
     "adsb_sweep": (c_int, [vp, c_int, c_int, c_int]),
     "adsb_step": (c_int, [vp, c_int, c_int, ctypes.POINTER(Substep), c_int, c_int]),

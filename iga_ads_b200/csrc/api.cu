@@ -226,7 +226,20 @@ void try_auto_segments(adsb_ctx* c, DevFactor& D) {
         return !e || atoi(e) != 0;
     }();
     if (!on || D.f.SC <= 32) return;
-    const int S = (D.n + 519) / 520;
+    // chunks per segment: as many as the tile kernel's shared memory holds (two ring slots of 16 lines, the
+    // factor tables of the segment, the chunk states) -- 29 chunks = 522 rows for p <= 2, fewer for wider bands
+    const int KL = D.f.KL, KD = D.f.KD;
+    int mc = 29;
+    for (; mc >= 6; --mc) {
+        const size_t rows = (size_t) mc * SWEEP_CH + KL + KD;
+        const size_t fixed = (size_t) mc * (KL + KD) * 16 + rows * (sweep_pitch(KL) + sweep_pitch(KD + 1) + sweep_pitch(KD + KL)) +
+                             (size_t) mc * (KL * KL + KD * KD) * SWEEP_MAX_DEPTH_DEV;
+        const size_t tile = ((size_t) mc * SWEEP_CH + KL + 8) * 16;
+        if ((fixed + 2 * tile) * 8 + 1024 <= 222 * 1024) break;
+    }
+    if (mc < 6) return;
+    const int seg_rows = mc * SWEEP_CH - 2;
+    const int S = (D.n + seg_rows - 1) / seg_rows;
     std::vector<int> bounds(S + 1);
     const std::string keep = g_last_error;
     if (pick_segment_bounds(D.n, D.kl, D.ipiv.data(), S, 2, std::max(D.kl + D.ku, 2), bounds.data()) == ADSB_OK) {
@@ -1078,6 +1091,40 @@ int adsb_norm(adsb_ctx* c, int b, int kind, int ref, double t, const double* ref
     c->launches += 2;
     out2[0] = std::sqrt(h[0]);
     out2[1] = std::sqrt(h[1]);
+    return ADSB_OK;
+}
+
+int adsb_project_values(adsb_ctx* c, int dst, int ez_lo, int ez_cnt, const double* values, int accumulate) {
+    if (!c || !values) return fail(ADSB_EINVAL, "project_values: null argument");
+    for (int d = 0; d < c->ndim; ++d)
+        if (c->cnt[d] != c->ng[d]) return fail(ADSB_ESTATE, "project_values: the context must own the whole domain");
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, dst)) return rc;
+    QuadAxes A;
+    if (int rc = quad_axes(c, A)) return rc;
+    const bool d3 = c->ndim == 3;
+    if (!d3) {
+        ez_lo = 0;
+        ez_cnt = 1;
+    } else if (ez_cnt <= 0) {  // the whole domain
+        ez_lo = 0;
+        ez_cnt = A.ne[2];
+    }
+    if (ez_lo < 0 || ez_cnt < 1 || (d3 && ez_lo + ez_cnt > A.ne[2])) return fail(ADSB_EINVAL, "project_values: bad element slab");
+    const size_t count = (size_t) A.ne[0] * A.q[0] * A.ne[1] * A.q[1] * (d3 ? (size_t) ez_cnt * A.q[2] : 1);
+    double* d_tab = nullptr;
+    CU(cudaMalloc((void**) &d_tab, count * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_tab, values, count * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    {
+        StageTimer t(c, 4);
+        if (e == cudaSuccess)
+            e = (cudaError_t) launch_project_tab(A, d_tab, ez_lo, ez_cnt, accumulate, c->buf[dst], c->cnt, c->stream, c->pitch0());
+    }
+    const cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(d_tab);
+    if (e != cudaSuccess) return cuda_fail(e, "project_values kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "project_values kernel");
+    c->launches++;
     return ADSB_OK;
 }
 

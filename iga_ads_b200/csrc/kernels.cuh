@@ -170,6 +170,9 @@ struct QuadAxes {
 // pitch0: doubles between consecutive x rows of `out` (0: dense, n[0])
 int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], const int n[3], cudaStream_t st,
                    long long pitch0 = 0);
+// f tabulated at the quadrature points of the z-element slab [ez_lo, ez_lo + ez_cnt) (device array)
+int launch_project_tab(const QuadAxes& A, const double* tab, int ez_lo, int ez_cnt, int accumulate, double* out,
+                       const int n[3], cudaStream_t st, long long pitch0 = 0);
 int launch_element_source(int src, const QuadAxes& A, double* G, const int elo[3], const int en[3], cudaStream_t st);
 int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int elo[3], const int en[3],
                    const int lo[3], const int n[3], cudaStream_t st, long long pitch0 = 0);

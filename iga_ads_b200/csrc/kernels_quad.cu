@@ -80,6 +80,44 @@ __global__ void project_kernel(const QuadAxes A, double* out, int lo0, int lo1, 
     out[i0 + pitch0 * (i1 + (long long) n1 * i2)] = acc;
 }
 
+// The same projection with f tabulated by the caller at the quadrature points of the z-element slab
+// [ez_lo, ez_lo + ez_cnt) (2-D: the whole domain): tab[(e0*q0+k0) + nq0*((e1*q1+k1) + nq1*((e2-ez_lo)*q2+k2))].
+// accumulate: add to `out` (the caller walks the slabs in ascending order); a single slab covering all z
+// elements reproduces the reference's summation order exactly.
+__global__ void project_tab_kernel(const QuadAxes A, const double* __restrict__ tab, int ez_lo, int ez_cnt, int accumulate,
+                                   double* out, int n0, int n1, int n2, long long pitch0) {
+    const int a0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a1 = blockIdx.y, a2 = blockIdx.z;
+    if (a0 >= n0) return;
+    const bool d3 = A.ndim == 3;
+    const int p0 = A.p[0], p1 = A.p[1], p2 = d3 ? A.p[2] : 0;
+    const int q0 = A.q[0], q1 = A.q[1], q2 = d3 ? A.q[2] : 1;
+    const int st0 = A.st[0], st1 = A.st[1], st2 = d3 ? A.st[2] : 0;
+    const long long nq0 = (long long) A.ne[0] * q0, nq1 = (long long) A.ne[1] * q1;
+    const int e2a = d3 ? max(max(a2 - p2, 0), ez_lo) : 0;
+    const int e2b = d3 ? min(min(a2, A.ne[2] - 1), ez_lo + ez_cnt - 1) : 0;
+    double acc = 0.0;
+    for (int e0 = max(a0 - p0, 0); e0 <= min(a0, A.ne[0] - 1); ++e0)
+        for (int e1 = max(a1 - p1, 0); e1 <= min(a1, A.ne[1] - 1); ++e1)
+            for (int e2 = e2a; e2 <= e2b; ++e2) {
+                const double J = d3 ? __dmul_rn(__dmul_rn(A.J[0][e0], A.J[1][e1]), A.J[2][e2])
+                                    : __dmul_rn(A.J[0][e0], A.J[1][e1]);
+                for (int k0 = 0; k0 < q0; ++k0)
+                    for (int k1 = 0; k1 < q1; ++k1)
+                        for (int k2 = 0; k2 < q2; ++k2) {
+                            const double w = d3 ? __dmul_rn(__dmul_rn(A.w[0][k0], A.w[1][k1]), A.w[2][k2])
+                                                : __dmul_rn(A.w[0][k0], A.w[1][k1]);
+                            double B = A.bt[0][(e0 * q0 + k0) * st0 + (a0 - e0)];
+                            B = __dmul_rn(B, A.bt[1][(e1 * q1 + k1) * st1 + (a1 - e1)]);
+                            if (d3) B = __dmul_rn(B, A.bt[2][(e2 * q2 + k2) * st2 + (a2 - e2)]);
+                            const double f = tab[(e0 * q0 + k0) + nq0 * ((e1 * q1 + k1) + nq1 * (long long) ((e2 - ez_lo) * q2 + k2))];
+                            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(__dmul_rn(f, B), w), J));
+                        }
+            }
+    double* o = out + a0 + pitch0 * (a1 + (long long) n1 * a2);
+    *o = accumulate ? __dadd_rn(*o, acc) : acc;
+}
+
 // G[e] = sum_q f(x_q) w J over the element box [elo, elo+en)
 template <int SRC>
 __global__ void element_source_kernel(const QuadAxes A, double* G, int elo0, int elo1, int elo2, int en0, int en1,
@@ -132,6 +170,14 @@ int launch_project(int src, const QuadAxes& A, double* out, const int lo[3], con
     case 3: project_kernel<3><<<grid, block, 0, st>>>(A, out, lo[0], lo[1], lo[2], n[0], n[1], n[2], pitch0); break;
     default: return (int) cudaErrorInvalidValue;
     }
+    return (int) cudaGetLastError();
+}
+
+int launch_project_tab(const QuadAxes& A, const double* tab, int ez_lo, int ez_cnt, int accumulate, double* out,
+                       const int n[3], cudaStream_t st, long long pitch0) {
+    if (pitch0 <= 0) pitch0 = n[0];
+    dim3 block(128, 1, 1), grid((n[0] + 127) / 128, n[1], n[2]);
+    project_tab_kernel<<<grid, block, 0, st>>>(A, tab, ez_lo, ez_cnt, accumulate, out, n[0], n[1], n[2], pitch0);
     return (int) cudaGetLastError();
 }
 

@@ -134,6 +134,11 @@ class Context:
                                  d_(out)))
         return float(out[0]), float(out[1])
 
+    def project_values(self, dst, values, ez_lo=0, ez_cnt=None, accumulate=False):
+        """L2-projection right-hand side of a function tabulated at the quadrature points (adsb_project_values)"""
+        v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        check(self.lib.adsb_project_values(self.h, dst, ez_lo, ez_cnt or 0, d_(v), int(accumulate)))
+
     def solve(self, buf, slots=None):
         s = np.array(list(slots or ()) + [0] * (3 - len(slots or ())), dtype=np.int32)
         check(self.lib.adsb_solve(self.h, buf, i_(s)))

@@ -197,6 +197,14 @@ int adsb_sample(adsb_ctx* ctx, int buf, const int* npts, const double* const* po
  * nqy*(ez*q+kz))] (host memory; L2 only).  The context must own the whole domain; the call synchronises. */
 int adsb_norm(adsb_ctx* ctx, int buf, int kind, int ref, double t, const double* ref_values, double* out2);
 
+/* The same projection for ANY function: the caller tabulates f at the quadrature points (host memory, x fastest:
+ * values[(ex*q+kx) + nqx*((ey*q+ky) + nqy*((ez-ez_lo)*q+kz))], nq = elements*q per axis) of the z-element slab
+ * [ez_lo, ez_lo+ez_cnt) (ignored in 2-D; ez_cnt <= 0: all z elements) -- a slab at a time keeps the table small (the whole 512^3 problem
+ * would need 29 GB).  accumulate != 0 adds to dst (walk the slabs in ascending order); one call over all z
+ * elements reproduces the reference's summation order exactly (include/ads/projection.hpp:60-107), slab-wise
+ * accumulation differs by rounding only.  The call synchronises. */
+int adsb_project_values(adsb_ctx* ctx, int dst_buf, int ez_lo, int ez_cnt, const double* values, int accumulate);
+
 /* ---- ADS solve: one batched banded forward/back substitution per axis, in place.
  * Replaces ads::ads_solve(rhs, buffer, dims...) (include/ads/solver.hpp:35-41,:148-160,:222-226)
  * i.e. 3 x { lin::solve_with_factorized -> dgbtrs_ (include/ads/lin/band_solve.hpp:21-31) +
