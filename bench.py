@@ -364,6 +364,41 @@ def run_single(args, cfg, local_rank):
                "note": "per step: adsb_upload_async(input) | adsb_step | adsb_download_async(result) on three streams, "
                        "pinned host buffers; serial = the same three calls back to back on one stream"}
 
+    # ---- the general quadrature kernel (north star (a): pointwise forms by sum-factorised Gauss quadrature): its bound is
+    # the FP64 pipe, not HBM.  Timed alone on a 256^3 problem of the same form; flop model of SURVEY.md 8d:
+    # 2 (2 m^2 + 3 m^3 + 4 m^4) FMA-flops + 10 m^3 pointwise flops per DOF, m = p + 1.
+    quad = None
+    if nd == 3 and not args.no_quadrature:
+        try:
+            neq = min(ne, 256)
+            qs = ads.PROBLEMS[cfg["problem"]](p, neq, ads.timesteps_config(1, dt), method=ads.RHS_QUADRATURE, device=local_rank)
+            qs._context().set_stream(stream.cuda_stream)
+            qs.prepare_matrices()
+            nq = neq + p
+            qs.ctx.upload(U_PREV, synthetic_local((nq,) * 3, (0, 0, 0), (nq,) * 3))
+            form = qs.substeps()[0].form
+            for _ in range(2):
+                qs.ctx.compute_rhs(form, U_PREV, U)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            q0.record(stream)
+            for _ in range(5):
+                qs.ctx.compute_rhs(form, U_PREV, U)
+            q1.record(stream)
+            torch.cuda.synchronize()
+            qms = q0.elapsed_time(q1) / 5
+            m = p + 1
+            flop_per_dof = 2 * 2 * (2 * m ** 2 + 3 * m ** 3 + 4 * m ** 4) + 10 * m ** 3
+            fp64_peak = 37.0  # TFLOP/s, measured FMA-chain peak of this pool's B200 (profiles/r1_ubench_fp64.txt)
+            tf = flop_per_dof * nq ** 3 / (qms * 1e-3) / 1e12
+            quad = {"kernel": "quad_rhs_kernel (ADSB_RHS_QUADRATURE: zero + element quadrature with atomic scatter)",
+                    "elements": neq, "dof": nq ** 3, "ms": qms, "dof_per_s": nq ** 3 / (qms * 1e-3),
+                    "flop_per_dof_model": flop_per_dof, "tflops": tf, "bound": "fp64", "peak_tflops": fp64_peak,
+                    "frac": tf / fp64_peak}
+            qs.ctx.close()
+        except Exception as e:  # noqa: BLE001 -- an extra record; never lose the bench line over it
+            quad = {"error": str(e)}
+
     out = {
         "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -376,6 +411,8 @@ def run_single(args, cfg, local_rank):
                    "parallelism": "1 GPU"},
         "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "finite": state_ok, "checksum": checksum,
     }
+    if quad:
+        out["rhs_quadrature"] = quad
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline:
@@ -396,6 +433,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-quadrature", action="store_true")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.p:

@@ -123,29 +123,105 @@ public:
         rhs.device_written();
     }
 
-    // L2-projection right-hand side (include/ads/projection.hpp:12-153), host loop in the reference's
-    // order: u_a = sum_e sum_q f(x_q) B_a(x_q) w J
+    // L2-projection right-hand side  u_a = sum_e sum_q f(x_q) B_a(x_q) w J  (include/ads/projection.hpp:12-153).
+    // f is a host callable, so it is evaluated on the host -- once per quadrature point, in slabs of z elements
+    // that keep the table of values below ~256 MB -- and the sum itself runs on the device
+    // (adsb_project_values; one slab reproduces the reference's summation order exactly).  No list of element
+    // index tuples is built (the reference's elements() range at 512^3 would be 1.6 GB as a vector).
     template <typename Function>
     void projection(vector_type& v, Function f) {
-        zero(v);
-        for (auto e : elements()) {
-            const double J = jacobian(e);
-            for (auto q : quad_points()) {
-                const double w = weight(q);
-                const auto x = point(e, q);
-                double fx;
-                if constexpr (D == 2)
-                    fx = f(x[0], x[1]);
-                else
-                    fx = f(x[0], x[1], x[2]);
-                for (auto a : dofs_on_element(e)) {
-                    const value_type B = eval_basis(e, q, a);
-                    v_at(v, a) += fx * B.val * w * J;
+        on_device(v);
+        std::size_t nq[3] = {1, 1, 1};
+        for (std::size_t d = 0; d < D; ++d) nq[d] = static_cast<std::size_t>(dims_[d].elements) * dims_[d].basis.quad_order;
+        const int qz = D == 3 ? dims_[D - 1].basis.quad_order : 1;
+        const int nez = D == 3 ? dims_[D - 1].elements : 1;
+        const std::size_t per_elem = nq[0] * nq[1] * qz;
+        const int slab = static_cast<int>(std::max<std::size_t>(1, std::min<std::size_t>(nez, (std::size_t{1} << 25) / per_elem)));
+        std::vector<double> tab(per_elem * slab);
+        for (int e0 = 0; e0 < nez; e0 += slab) {
+            const int cnt = std::min(slab, nez - e0);
+            for (int kz = 0; kz < cnt * qz; ++kz) {
+                const double z = D == 3 ? dims_[D - 1].basis.x_flat[static_cast<std::size_t>(e0) * qz + kz] : 0.0;
+                for (std::size_t ky = 0; ky < nq[1]; ++ky) {
+                    const double y = dims_[1].basis.x_flat[ky];
+                    double* row = tab.data() + (static_cast<std::size_t>(kz) * nq[1] + ky) * nq[0];
+                    for (std::size_t kx = 0; kx < nq[0]; ++kx) {
+                        const double x = dims_[0].basis.x_flat[kx];
+                        if constexpr (D == 2)
+                            row[kx] = f(x, y);
+                        else
+                            row[kx] = f(x, y, z);
+                    }
                 }
             }
+            device::check(adsb_project_values(dev().handle(), v.device_buffer(), e0, cnt, tab.data(), e0 > 0 ? 1 : 0));
         }
+        v.device_written();
     }
 
+    // basic_simulation_Nd::normL2 / normH1 (include/ads/simulation/basic_simulation_3d.hpp:314-330) on the device
+    double normL2(vector_type& u) { return norm_impl(u, 0, 0, 0.0, nullptr)[0]; }
+    double normH1(vector_type& u) { return norm_impl(u, 1, 0, 0.0, nullptr)[0]; }
+    // errorL2 against a host callable (basic_simulation_3d.hpp:380-398): f is tabulated at the quadrature points
+    template <typename Function>
+    double errorL2(vector_type& u, Function f) {
+        std::size_t nq[3] = {1, 1, 1};
+        for (std::size_t d = 0; d < D; ++d) nq[d] = static_cast<std::size_t>(dims_[d].elements) * dims_[d].basis.quad_order;
+        std::vector<double> tab(nq[0] * nq[1] * nq[2]);
+        for (std::size_t kz = 0; kz < nq[2]; ++kz)
+            for (std::size_t ky = 0; ky < nq[1]; ++ky)
+                for (std::size_t kx = 0; kx < nq[0]; ++kx) {
+                    const double x = dims_[0].basis.x_flat[kx], y = dims_[1].basis.x_flat[ky];
+                    double& t = tab[kx + nq[0] * (ky + nq[1] * kz)];
+                    if constexpr (D == 2)
+                        t = f(x, y);
+                    else
+                        t = f(x, y, dims_[2].basis.x_flat[kz]);
+                }
+        return norm_impl(u, 0, 2, 0.0, tab.data())[0];
+    }
+    // {error, norm of the reference} against the validation solution sin(pi x) sin(pi y) [sin(pi z)] exp(-d pi^2 t)
+    // (examples/validation/validation.hpp:45-55,:121-129); h1: H1 instead of L2
+    std::array<double, 2> error_validation(vector_type& u, double t, bool h1) { return norm_impl(u, h1 ? 1 : 0, 1, t, nullptr); }
+
+    // output_manager<D>::evaluate (include/ads/output_manager.hpp:66-73,:101-118): the spline on intervals + 1
+    // points per axis; values come back first index fastest, the order the reference's writers print them in
+    std::vector<double> sample(vector_type& u, int intervals) {
+        on_device(u);
+        u.to_device();
+        int npts[3] = {1, 1, 1};
+        std::vector<std::vector<double>> pts(D), kn(D);
+        const double* pp[3] = {nullptr, nullptr, nullptr};
+        const double* kp[3] = {nullptr, nullptr, nullptr};
+        std::size_t total = 1;
+        for (std::size_t d = 0; d < D; ++d) {
+            npts[d] = intervals + 1;
+            pts[d].resize(npts[d]);
+            for (int i = 0; i <= intervals; ++i) {  // ads::linspace -> lerp(i, n, a, b)
+                const double t = static_cast<double>(i) / static_cast<double>(intervals);
+                pts[d][i] = (1 - t) * dims_[d].a + t * dims_[d].b;
+            }
+            kn[d].resize(dims_[d].elements + 2 * dims_[d].p + 1);
+            device::check(adsb_knots(dims_[d].p, dims_[d].elements, dims_[d].a, dims_[d].b, kn[d].data()));
+            pp[d] = pts[d].data();
+            kp[d] = kn[d].data();
+            total *= static_cast<std::size_t>(npts[d]);
+        }
+        std::vector<double> out(total);
+        device::check(adsb_sample(dev().handle(), u.device_buffer(), npts, pp, kp, out.data()));
+        return out;
+    }
+
+private:
+    std::array<double, 2> norm_impl(vector_type& u, int kind, int ref, double t, const double* tab) {
+        on_device(u);
+        u.to_device();
+        std::array<double, 2> out{};
+        device::check(adsb_norm(dev().handle(), u.device_buffer(), kind, ref, t, tab, out.data()));
+        return out;
+    }
+
+public:
     // ---- per-element helpers (simulation_3d.hpp:64-136, simulation_2d.hpp:61-131)
     std::vector<index_type> elements() const {
         index_type lo{}, hi{};

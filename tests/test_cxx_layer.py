@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EX = os.path.join(ROOT, "iga_ads_b200", "examples")
-PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d")
+PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check")
 
 
 def build():
@@ -68,3 +68,13 @@ def test_examples_match_reference_golden(golden, prog, args, name, p, ne, dt, st
     assert r.returncode == 0, r.stderr
     want = golden["problems"][f"{name}_p{p}_n{ne}_shipped"]
     assert abs(checksum(r.stdout) - want.sum()) < 1e-9 * max(1.0, np.abs(want).sum())
+
+
+@pytest.mark.gpu
+def test_surface_check_value_semantics_projection_norms_sampling():
+    """lin::tensor copies taken from a device-resident tensor, buffer-id recycling over 3 x ADSB_MAX_BUFFERS
+    temporaries, projection of an arbitrary host callable on the device, errorL2 / normL2 / normH1, sample()"""
+    build()
+    r = run("surface_check", 12)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "surface_check OK" in r.stdout
