@@ -391,7 +391,7 @@ def run_single(args, cfg, local_rank):
             flop_per_dof = 2 * 2 * (2 * m ** 2 + 3 * m ** 3 + 4 * m ** 4) + 10 * m ** 3
             fp64_peak = 37.0  # TFLOP/s, measured FMA-chain peak of this pool's B200 (profiles/r1_ubench_fp64.txt)
             tf = flop_per_dof * nq ** 3 / (qms * 1e-3) / 1e12
-            quad = {"kernel": "quad_rhs_kernel (ADSB_RHS_QUADRATURE: zero + element quadrature with atomic scatter)",
+            quad = {"kernel": "quad_brick_kernel (ADSB_RHS_QUADRATURE: init + brick quadrature, 8 colour launches, deterministic)",
                     "elements": neq, "dof": nq ** 3, "ms": qms, "dof_per_s": nq ** 3 / (qms * 1e-3),
                     "flop_per_dof_model": flop_per_dof, "tflops": tf, "bound": "fp64", "peak_tflops": fp64_peak,
                     "frac": tf / fp64_peak}

@@ -43,6 +43,30 @@ class Form(ctypes.Structure):
         return cls(alpha, (c_dbl * 3)(*b), gamma, forcing_buf, method, source)
 
 
+POINT_LINEAR = 0
+POINT_FLOW = 1
+
+
+class PointForm(ctypes.Structure):
+    """adsb_point_form: the integrand of the general quadrature right-hand side (include/adsb200.h)."""
+    _fields_ = [("kind", c_int), ("alpha", c_dbl), ("beta", c_dbl * 3), ("adv", c_dbl * 3), ("gamma", c_dbl),
+                ("source", c_int), ("source_plain", c_int), ("par", c_dbl * 4), ("forcing_buf", c_int),
+                ("forcing_scale", c_dbl)]
+
+    @classmethod
+    def linear(cls, alpha=1.0, beta=(0.0, 0.0, 0.0), adv=(0.0, 0.0, 0.0), gamma=0.0, source=0, source_plain=False,
+               forcing_buf=-1, forcing_scale=0.0):
+        b = list(beta) + [0.0] * (3 - len(beta))
+        a = list(adv) + [0.0] * (3 - len(adv))
+        return cls(POINT_LINEAR, alpha, (c_dbl * 3)(*b), (c_dbl * 3)(*a), gamma, source, int(source_plain),
+                   (c_dbl * 4)(), forcing_buf, forcing_scale)
+
+    @classmethod
+    def flow(cls, dt, mi=10.0):
+        """examples/flow/flow.hpp:74-101; the permeability table goes in with Context.set_point_coefficient"""
+        return cls(POINT_FLOW, 1.0, (c_dbl * 3)(), (c_dbl * 3)(), dt, 2, 0, (c_dbl * 4)(dt, mi, 0.0, 0.0), -1, 0.0)
+
+
 class Substep(ctypes.Structure):
     _fields_ = [("form", Form), ("slots", c_int * 3), ("fix_axis", c_int), ("fix_buf", c_int)]
 
@@ -111,6 +135,10 @@ _SIGNATURES = {
     "adsb_row_pitch": (c_ll, [vp]),
     "adsb_set_plane": (c_int, [vp, c_int, c_int, c_int, dp]),
     "adsb_compute_rhs": (c_int, [vp, ctypes.POINTER(Form), c_int, c_int]),
+    "adsb_set_line_factors": (c_int, [vp, c_int, c_int, c_int, dp, ip]),
+    "adsb_solve_special": (c_int, [vp, c_int, c_int, ip]),
+    "adsb_set_point_coefficient": (c_int, [vp, dp]),
+    "adsb_compute_rhs_pointwise": (c_int, [vp, ctypes.POINTER(PointForm), c_int, c_int]),
     "adsb_load_tensor": (c_int, [vp, c_int, c_int, c_int]),
     "adsb_project_init": (c_int, [vp, c_int, c_int]),
     "adsb_sample": (c_int, [vp, c_int, ip, ctypes.POINTER(dp), ctypes.POINTER(dp), dp]),

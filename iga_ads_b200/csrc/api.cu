@@ -84,6 +84,15 @@ struct adsb_ctx {
     std::vector<cudaEvent_t> seg_events;  // [0] fork, [1 + i] join of stream i
     double* seg_scratch = nullptr;
     size_t seg_scratch_doubles = 0;
+    double* point_coef = nullptr;  // adsb_set_point_coefficient: coefficient table at the quadrature points
+    // generalised ADS: per-line factors of one axis (adsb_set_line_factors), device layout [j][r][line]
+    struct LineFactors {
+        double* ab = nullptr;
+        int* ipiv = nullptr;
+        double* scratch = nullptr;  // x axis only: the transposed line set
+        int p = 0, n = 0;
+        long long lines = 0;
+    } line_fac[3];
     // Managed tensors keep the reference's index order (x fastest) but pad every x row to an EVEN number of
     // doubles: rows, planes and the tensor itself then start 16 B aligned, which is what the TMA-fed
     // kernels need (n = elements + p is odd for every odd degree).  The pad column is never read as data.
@@ -621,6 +630,12 @@ int adsb_destroy(adsb_ctx* c) {
     for (auto st : c->seg_streams) cudaStreamDestroy(st);
     for (auto e : c->seg_events) cudaEventDestroy(e);
     cudaFree(c->seg_scratch);
+    cudaFree(c->point_coef);
+    for (auto& lf : c->line_fac) {
+        cudaFree(lf.ab);
+        cudaFree(lf.ipiv);
+        cudaFree(lf.scratch);
+    }
     if (c->side.side) {
         cudaStreamDestroy(c->side.side);
         cudaEventDestroy(c->side.fork);
@@ -868,6 +883,153 @@ int adsb_compute_rhs(adsb_ctx* c, const adsb_form* f, int src, int dst) {
     }
     adsb_view v = local_view(c);
     return rhs_impl(c, *f, c->buf[src], v, c->lo, forcing, c->buf[dst], v, c->lo);
+}
+
+// ---- general pointwise forms (brick quadrature kernel, quadbrick.cuh)
+int adsb_set_point_coefficient(adsb_ctx* c, const double* values) {
+    if (!c || !values) return fail(ADSB_EINVAL, "set_point_coefficient: null argument");
+    if (int rc = select_device(c)) return rc;
+    size_t count = 1;
+    for (int d = 0; d < c->ndim; ++d) {
+        if (!c->ax[d].tables) return fail(ADSB_ESTATE, "set_point_coefficient: axis tables not uploaded");
+        if (c->cnt[d] != c->ng[d]) return fail(ADSB_ESTATE, "set_point_coefficient: the context must own the whole domain");
+        count *= (size_t) c->ax[d].elements * c->ax[d].q;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->point_coef);
+    c->point_coef = nullptr;
+    CU(cudaMalloc((void**) &c->point_coef, count * sizeof(double)));
+    CU(cudaMemcpy(c->point_coef, values, count * sizeof(double), cudaMemcpyHostToDevice));
+    return ADSB_OK;
+}
+
+int adsb_compute_rhs_pointwise(adsb_ctx* c, const adsb_point_form* f, int src, int dst) {
+    if (!c || !f) return fail(ADSB_EINVAL, "compute_rhs_pointwise: null argument");
+    if (src == dst) return fail(ADSB_EINVAL, "compute_rhs_pointwise: src and dst must differ");
+    if (src < 0 || src >= ADSB_MAX_BUFFERS || !c->buf[src]) return fail(ADSB_ESTATE, "compute_rhs_pointwise: src not allocated");
+    if (f->kind != ADSB_POINT_LINEAR && f->kind != ADSB_POINT_FLOW) return fail(ADSB_EINVAL, "compute_rhs_pointwise: unknown form");
+    if (f->source < 0 || f->source > 2) return fail(ADSB_EINVAL, "compute_rhs_pointwise: unknown source");
+    if (f->kind == ADSB_POINT_FLOW) {
+        if (c->ndim != 3) return fail(ADSB_EINVAL, "compute_rhs_pointwise: the flow form is 3-D");
+        if (c->ax[0].p > 3) return fail(ADSB_EINVAL, "compute_rhs_pointwise: the flow form is built for p <= 3");
+        if (!c->point_coef) return fail(ADSB_ESTATE, "compute_rhs_pointwise: no coefficient table (adsb_set_point_coefficient)");
+    }
+    if (int rc = select_device(c)) return rc;
+    if (int rc = ensure_buf(c, dst)) return rc;
+    QuadAxes A;
+    if (int rc = quad_axes(c, A)) return rc;
+    const adsb_view v = local_view(c);
+    RhsGeom g{};
+    g.in = c->buf[src];
+    g.out = c->buf[dst];
+    int elo[3] = {0, 0, 0}, en[3] = {1, 1, 1};
+    for (int d = 0; d < 3; ++d) {
+        g.si[d] = g.so[d] = v.s[d];
+        g.in_lo[d] = g.out_lo[d] = c->lo[d];
+        g.in_n[d] = g.out_n[d] = v.n[d];
+        if (d < c->ndim) {
+            if (c->cnt[d] != c->ng[d]) return fail(ADSB_ESTATE, "compute_rhs_pointwise: the context must own the whole domain");
+            if (c->ax[d].q != c->ax[d].p + 1 || c->ax[d].ders != 1 || c->ax[d].p != c->ax[0].p)
+                return fail(ADSB_EINVAL, "compute_rhs_pointwise: needs the same p on every axis, quad_order = p + 1, derivatives = 1");
+            en[d] = c->ax[d].elements;
+        }
+    }
+    if (f->forcing_buf >= 0) {
+        if (f->forcing_buf >= ADSB_MAX_BUFFERS || !c->buf[f->forcing_buf]) return fail(ADSB_ESTATE, "compute_rhs_pointwise: forcing buffer not allocated");
+        g.forcing = c->buf[f->forcing_buf];
+        g.gamma = f->forcing_scale;
+    }
+    g.max_sms = c->sm_limit;
+    PointFormArgs pf{};
+    pf.kind = f->kind;
+    pf.alpha = f->alpha;
+    for (int d = 0; d < 3; ++d) {
+        pf.beta[d] = d < c->ndim ? f->beta[d] : 0.0;
+        pf.adv[d] = d < c->ndim ? f->adv[d] : 0.0;
+    }
+    pf.gamma = f->gamma;
+    pf.source = f->gamma != 0.0 ? f->source : 0;
+    pf.plain = f->source_plain;
+    for (int i = 0; i < 4; ++i) pf.par[i] = f->par[i];
+    StageTimer t(c, 0);
+    int nl = 0;
+    cudaError_t e = (cudaError_t) launch_rhs_brick(c->ndim, A, g, pf, elo, en, c->point_coef, c->stream, &nl);
+    c->launches += nl;
+    if (e != cudaSuccess) return cuda_fail(e, "pointwise rhs kernels");
+    return ADSB_OK;
+}
+
+// ---- generalised ADS: one axis with a different factor per line (include/ads/solver.hpp:56-96,:170-195)
+int adsb_set_line_factors(adsb_ctx* c, int axis, int kl, int ku, const double* ab_lines, const int* ipiv_lines) {
+    if (!c || !ab_lines || !ipiv_lines) return fail(ADSB_EINVAL, "set_line_factors: null argument");
+    if (axis < 0 || axis >= c->ndim) return fail(ADSB_EINVAL, "set_line_factors: bad axis");
+    if (kl != ku || kl < 1 || kl > 5) return fail(ADSB_EINVAL, "set_line_factors: needs kl = ku = p, 1 <= p <= 5");
+    for (int d = 0; d < c->ndim; ++d)
+        if (c->cnt[d] != c->ng[d]) return fail(ADSB_ESTATE, "set_line_factors: the context must own the whole domain");
+    if (int rc = select_device(c)) return rc;
+    const int n = c->ng[axis], ld = 2 * kl + ku + 1;
+    long long lines = 1;
+    for (int d = 0; d < c->ndim; ++d)
+        if (d != axis) lines *= c->ng[d];
+    // [line][j][r] -> [j][r][line]; pivots 1-based -> 0-based rows
+    std::vector<double> ab((size_t) lines * n * ld);
+    std::vector<int> pv((size_t) lines * n);
+    for (long long l = 0; l < lines; ++l)
+        for (int j = 0; j < n; ++j) {
+            for (int r = 0; r < ld; ++r) ab[((size_t) j * ld + r) * lines + l] = ab_lines[((size_t) l * n + j) * ld + r];
+            const int pr = ipiv_lines[(size_t) l * n + j] - 1;
+            if (pr < j || pr > std::min(n - 1, j + kl)) return fail(ADSB_EINVAL, "set_line_factors: pivot index out of range");
+            pv[(size_t) j * lines + l] = pr;
+        }
+    auto& lf = c->line_fac[axis];
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(lf.ab);
+    cudaFree(lf.ipiv);
+    cudaFree(lf.scratch);
+    lf = adsb_ctx::LineFactors{};
+    CU(cudaMalloc((void**) &lf.ab, ab.size() * sizeof(double)));
+    CU(cudaMalloc((void**) &lf.ipiv, pv.size() * sizeof(int)));
+    CU(cudaMemcpy(lf.ab, ab.data(), ab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(lf.ipiv, pv.data(), pv.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (axis == 0) CU(cudaMalloc((void**) &lf.scratch, (size_t) ((lines + 31) / 32) * 32 * n * sizeof(double)));
+    lf.p = kl;
+    lf.n = n;
+    lf.lines = lines;
+    return ADSB_OK;
+}
+
+int adsb_solve_special(adsb_ctx* c, int b, int special_axis, const int* slots) {
+    if (!c) return fail(ADSB_EINVAL, "null context");
+    if (b < 0 || b >= ADSB_MAX_BUFFERS || !c->buf[b]) return fail(ADSB_ESTATE, "solve_special: buffer not allocated");
+    if (special_axis < 0 || special_axis >= c->ndim) return fail(ADSB_EINVAL, "solve_special: bad axis");
+    const auto& lf = c->line_fac[special_axis];
+    if (!lf.ab) return fail(ADSB_ESTATE, "solve_special: no line factors on this axis (adsb_set_line_factors)");
+    if (int rc = select_device(c)) return rc;
+    const long long pitch = c->pitch0(), ny = c->cnt[1];
+    {
+        StageTimer t(c, 1 + special_axis);
+        int L0 = c->cnt[0];
+        long long s0 = 1, s1 = 0, sj = 0;
+        if (special_axis == 0) {
+            s0 = pitch;  // rows are the lines
+        } else if (special_axis == 1) {
+            s1 = pitch * ny;
+            sj = pitch;
+        } else {
+            s1 = pitch;
+            sj = pitch * ny;
+        }
+        cudaError_t e = (cudaError_t) launch_line_sweep(lf.p, c->buf[b], lf.ab, lf.ipiv, lf.n, lf.lines, special_axis, L0, s0, s1,
+                                                        sj, lf.scratch, c->stream);
+        c->launches++;
+        if (e != cudaSuccess) return cuda_fail(e, "line sweep kernel");
+    }
+    // the other axes, in order, with their ordinary factors (the reference solves the special dimension first)
+    for (int d = 0; d < c->ndim; ++d) {
+        if (d == special_axis) continue;
+        if (int rc = adsb_sweep(c, b, d, slots ? slots[d] : 0)) return rc;
+    }
+    return ADSB_OK;
 }
 
 int adsb_rhs_view(adsb_ctx* c, const adsb_form* f, const double* in, const adsb_view* vin, const int* in_lo,

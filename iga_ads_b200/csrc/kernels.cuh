@@ -183,7 +183,22 @@ int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int el
 int launch_rhs_quadrature(int ndim, const QuadAxes& A, const RhsGeom& g, int source, const int elo[3], const int en[3],
                           cudaStream_t st);
 int launch_zero_box(double* y, const int n[3], const long long s[3], cudaStream_t st);
+// Pointwise form of the brick quadrature kernel (quadbrick.cuh); mirrors adsb_point_form.
+struct PointFormArgs {
+    int kind;  // 0 linear (+ advection, built-in source), 1 flow (nonlinear, tabulated coefficient)
+    double alpha, beta[3], adv[3], gamma;
+    int source, plain;
+    double par[4];
+};
+// out box of g = g.gamma * g.forcing (or zero) + the quadrature sums of the elements [elo, elo + en); deterministic.
+// coef: per-point coefficient table of the whole domain (x fastest) for the forms that use one.
+int launch_rhs_brick(int ndim, const QuadAxes& A, const RhsGeom& g, const PointFormArgs& f, const int elo[3],
+                     const int en[3], const double* coef, cudaStream_t st, int* nlaunch);
 int launch_axpy_box(double* y, const double* x, double a, const int n[3], const long long s[3], cudaStream_t st);
+
+// Per-line factors (kernels_lines.cu): the special dimension of the generalised ADS.
+int launch_line_sweep(int p, double* t, const double* ab, const int* ipiv, int n, long long lines, int axis, int L0,
+                      long long s0, long long s1, long long sj, double* scratch, cudaStream_t st);
 
 // ---- segmented substitution (kernels_seg.cu; tables: build_segment_plan in host_setup.cpp)
 struct SegDev {

@@ -18,7 +18,7 @@
 // The per-axis tables b[e][q][d][i] are the reference's own (basis_data, src/ads/basis_data.cpp:63-114)
 // staged in shared memory per CTA.  ~1.7 kFMA per element at p=2: the bound is the FP64 pipe.
 // The sum over elements is not ordered (atomics): results vary in the last bits from run to run.
-#include "kernels.cuh"
+#include "quadbrick.cuh"
 
 namespace adsb {
 
@@ -270,6 +270,43 @@ int launch_axpy_box(double* y, const double* x, double a, const int n[3], const 
     dim3 block(128, 1, 1), grid((n[0] + 127) / 128, n[1], n[2]);
     axpy_kernel<<<grid, block, 0, st>>>(y, x, a, n[0], s[1], s[2], n[1], n[2]);
     return (int) cudaGetLastError();
+}
+
+// ---- brick kernel (quadbrick.cuh): the shipped path of ADSB_RHS_QUADRATURE and adsb_compute_rhs_pointwise
+namespace qb {
+__global__ void init_box_kernel(double* y, const double* x, double a, long long n0, long long s1, long long s2) {
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    const long long o = i + blockIdx.y * s1 + blockIdx.z * s2;
+    y[o] = x ? a * x[o] : 0.0;
+}
+}  // namespace qb
+
+int launch_rhs_brick(int ndim, const QuadAxes& A, const RhsGeom& g, const PointFormArgs& f, const int elo[3],
+                     const int en[3], const double* coef, cudaStream_t st, int* nlaunch) {
+    const int p = A.p[0];
+    for (int d = 0; d < ndim; ++d)
+        if (A.p[d] != p || A.q[d] != p + 1 || A.st[d] != 2 * (p + 1)) return (int) cudaErrorInvalidValue;
+    {
+        const int n0 = g.out_n[0], n1 = g.out_n[1], n2 = ndim == 3 ? g.out_n[2] : 1;
+        if (g.so[0] != 1) return (int) cudaErrorInvalidValue;
+        dim3 block(128, 1, 1), grid((n0 + 127) / 128, n1, n2);
+        qb::init_box_kernel<<<grid, block, 0, st>>>(g.out, g.gamma != 0.0 ? g.forcing : nullptr, g.gamma, n0, g.so[1],
+                                                    ndim == 3 ? g.so[2] : 0);
+        if (nlaunch) ++*nlaunch;
+    }
+    if (f.kind == 1) {
+        if (ndim != 3 || !coef) return (int) cudaErrorInvalidValue;
+        qb::FormFlow form{f.par[0], f.par[1]};
+        return qb::launch_brick_form<qb::FormFlow>(ndim, A, g, form, elo, en, coef, g.max_sms, st, nlaunch);
+    }
+    if (f.kind != 0) return (int) cudaErrorInvalidValue;
+    if (f.source && f.plain) {
+        qb::FormLinear<true> form{f.alpha, {f.beta[0], f.beta[1], f.beta[2]}, {f.adv[0], f.adv[1], f.adv[2]}, f.gamma, f.source};
+        return qb::launch_brick_form<qb::FormLinear<true>>(ndim, A, g, form, elo, en, nullptr, g.max_sms, st, nlaunch);
+    }
+    qb::FormLinear<false> form{f.alpha, {f.beta[0], f.beta[1], f.beta[2]}, {f.adv[0], f.adv[1], f.adv[2]}, f.gamma, f.source};
+    return qb::launch_brick_form<qb::FormLinear<false>>(ndim, A, g, form, elo, en, nullptr, g.max_sms, st, nlaunch);
 }
 
 }  // namespace adsb

@@ -115,6 +115,15 @@ class Context:
     def compute_rhs(self, form, src, dst):
         check(self.lib.adsb_compute_rhs(self.h, ctypes.byref(form), src, dst))
 
+    def set_point_coefficient(self, values):
+        """coefficient table of the pointwise forms: one value per quadrature point of the domain, x fastest"""
+        v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        check(self.lib.adsb_set_point_coefficient(self.h, d_(v)))
+
+    def compute_rhs_pointwise(self, form, src, dst):
+        """general pointwise form by brick quadrature (adsb_compute_rhs_pointwise)"""
+        check(self.lib.adsb_compute_rhs_pointwise(self.h, ctypes.byref(form), src, dst))
+
     def load_tensor(self, source, with_test_function, dst):
         check(self.lib.adsb_load_tensor(self.h, source, int(with_test_function), dst))
 
@@ -142,6 +151,16 @@ class Context:
     def solve(self, buf, slots=None):
         s = np.array(list(slots or ()) + [0] * (3 - len(slots or ())), dtype=np.int32)
         check(self.lib.adsb_solve(self.h, buf, i_(s)))
+
+    def set_line_factors(self, axis, lus, ipivs, kl, ku):
+        """generalised ADS: lus[l] / ipivs[l] = band_factorize() output of line l's matrix along `axis`"""
+        ab = np.ascontiguousarray(lus, dtype=np.float64)
+        pv = np.ascontiguousarray(ipivs, dtype=np.int32)
+        check(self.lib.adsb_set_line_factors(self.h, axis, kl, ku, d_(ab), i_(pv)))
+
+    def solve_special(self, buf, special_axis, slots=None):
+        s = np.array(list(slots or ()) + [0] * (3 - len(slots or ())), dtype=np.int32)
+        check(self.lib.adsb_solve_special(self.h, buf, special_axis, i_(s)))
 
     def sweep(self, buf, axis, slot=0):
         check(self.lib.adsb_sweep(self.h, buf, axis, slot))
@@ -461,6 +480,46 @@ class scalability_2d(_scalability, simulation_2d):
         c = dim_config(p, elements)
         simulation_2d.__init__(self, c, c, steps, device=device)
         self.method = method
+
+
+class flow(simulation_3d):
+    """examples/flow/flow.hpp: nonlinear flow, rhs = (u v + dt (-k(x) exp(mi u) grad u . grad v + h v)) w J with the
+    permeability k tabulated at the quadrature points (fill_permeability_map, flow.hpp:53-60) -- a general
+    pointwise form: adsb_compute_rhs_pointwise(ADSB_POINT_FLOW) + ads_solve per step (flow.hpp:62-72).
+    `permeability` / `init_state`: callables f(x, y, z) on numpy arrays (the reference's are
+    environment::permeability, environment.hpp:78-88, and ads::bump(0.1, 0.5, .), flow.hpp:36-41), or tables."""
+
+    def __init__(self, p, elements, steps, permeability, init_state=None, mi=10.0, device=0):
+        c = dim_config(p, elements)
+        super().__init__(c, c, c, steps, device=device)
+        self.permeability, self.init_state, self.mi = permeability, init_state, mi
+
+    def quadrature_grid(self):
+        """coordinates of all quadrature points, shaped for broadcasting to [nqz, nqy, nqx]"""
+        x, y, z = (d.basis["x"].ravel() for d in self.dims)
+        return x[None, None, :], y[None, :, None], z[:, None, None]
+
+    def tabulate(self, f):
+        if callable(f):
+            x, y, z = self.quadrature_grid()
+            f = np.broadcast_to(f(x, y, z), (z.size, y.size, x.size))
+        return np.ascontiguousarray(f, dtype=np.float64)
+
+    def before(self):
+        self.prepare_matrices()
+        ctx = self._context()
+        ctx.set_point_coefficient(self.tabulate(self.permeability))
+        if self.init_state is not None:
+            ctx.project_values(U, self.tabulate(self.init_state))
+            self.solve(U)
+
+    def advance(self, nsteps):
+        ctx = self._context()
+        form = _lib.PointForm.flow(self.steps.dt, self.mi)
+        for _ in range(nsteps):
+            ctx.swap(U, U_PREV)                           # before_step
+            ctx.compute_rhs_pointwise(form, U_PREV, U)    # compute_rhs
+            self.solve(U)
 
 
 PROBLEMS = {"heat_3d": heat_3d, "heat_2d": heat_2d, "implicit_2d": implicit_2d,

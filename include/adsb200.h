@@ -165,6 +165,51 @@ typedef struct {
 } adsb_form;
 int adsb_compute_rhs(adsb_ctx* ctx, const adsb_form* form, int src_buf, int dst_buf);
 
+/* ---- generalised ADS: one "special" axis whose lines each have their own band matrix
+ * Replaces ads_solve(rhs, buf, dims...) with a callable among the dims (include/ads/solver.hpp:56-96,:170-195; the
+ * callable of examples/maxwell/maxwell_ads.hpp:139-163 solves line (i, j) with its own factorised matrix).
+ * adsb_set_line_factors: ab_lines[l][j][r] is the factor of line l exactly as adsb_band_factorize / dgbtrf_ leaves
+ * it (n columns of 2kl+ku+1 rows), ipiv_lines[l][j] its 1-based pivots; kl = ku = p <= 5.  Lines are numbered over
+ * the other axes in the tensor's own order (x fastest): axis 0: l = iy + ny*iz; axis 1: l = ix + nx*iz; axis 2:
+ * l = ix + nx*iy.  adsb_solve_special solves the special axis first (one dgbtrs recurrence per line, a thread per
+ * line), then the remaining axes with the factor slots slots[d], as the reference does. */
+int adsb_set_line_factors(adsb_ctx* ctx, int axis, int kl, int ku, const double* ab_lines, const int* ipiv_lines);
+int adsb_solve_special(adsb_ctx* ctx, int buf, int special_axis, const int* slots);
+
+/* ---- general pointwise forms: the element loop of compute_rhs() with an arbitrary integrand
+ *     rhs_a = [forcing_scale * F_a] + sum_e sum_q ( k0 v_a + k1 d_x v_a + k2 d_y v_a + k3 d_z v_a ) w J
+ * where k0..k3 are functions of the point, u_prev and grad u_prev there (include/ads/simulation/simulation_3d.hpp:
+ * 64-145: eval_fun / eval_basis / update_global_rhs; the model loop is examples/scalability/test3d.hpp:66-95).
+ * Evaluated by Gauss quadrature with sum factorisation over bricks of elements, FP64-bound, deterministic
+ * (csrc/quadbrick.cuh); the integrand is a template functor of the kernel, selected by `kind`:
+ *   ADSB_POINT_LINEAR  k0 = alpha u - adv . grad u + gamma f(x),  k_d = -beta[d] d_d u     (every form of
+ *                      adsb_form, plus the advection term of examples/pollution/pollution_3d.hpp);
+ *                      source: 0 none, 1 the scalability forcing (test3d.hpp:58-64), 2 the flow forcing
+ *                      (examples/flow/flow.hpp:124-128); source_plain 1: gamma f w J goes to every DOF of the
+ *                      element WITHOUT the test function, as test3d.hpp:86-88 does
+ *   ADSB_POINT_FLOW    examples/flow/flow.hpp:74-101 (nonlinear): k0 = u + dt h(x), k_d = -dt k(x) exp(mi u) d_d u
+ *                      with par[0] = dt, par[1] = mi, h = source 2 and k the table of adsb_set_point_coefficient
+ *                      (flow.hpp:53-60 fill_permeability_map); 3-D, p <= 3
+ * The context must own the whole domain, same degree on every axis, quad_order = p + 1, derivatives = 1. */
+#define ADSB_POINT_LINEAR 0
+#define ADSB_POINT_FLOW 1
+typedef struct {
+    int kind;
+    double alpha;
+    double beta[3];
+    double adv[3];
+    double gamma;
+    int source;
+    int source_plain;
+    double par[4];
+    int forcing_buf;       /* managed buffer holding a load tensor F, or -1 */
+    double forcing_scale;  /* its coefficient */
+} adsb_point_form;
+/* values (host): one double per quadrature point of the domain, x fastest:
+ * values[(ex*q+kx) + nqx*((ey*q+ky) + nqy*(ez*q+kz))], nq_d = elements_d * q_d */
+int adsb_set_point_coefficient(adsb_ctx* ctx, const double* values);
+int adsb_compute_rhs_pointwise(adsb_ctx* ctx, const adsb_point_form* form, int src_buf, int dst_buf);
+
 /* Load tensor of a built-in source: F_a = sum_{e in supp(a)} sum_q f(x_q) [v_a(x_q)] w J.
  * source 1: the scalability forcing (examples/scalability/test3d.hpp:58-64, test2d.hpp:49-54).
  * with_test_function 0 reproduces the reference form, which adds dt*f(x_q)*w*J to every DOF of

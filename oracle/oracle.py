@@ -206,6 +206,8 @@ class Ref(_Base):
                      "ref_scalability2d", "ref_implicit3d"):
             getattr(L, name).argtypes = [_c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int, _dp, _dp]
         L.ref_time_heat3d_hoisted.argtypes = [_c_int, _c_int, _c_dbl, _c_int, _dp, _dp]
+        if hasattr(L, "ref_flow"):
+            L.ref_flow.argtypes = [_c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int, _dp, _dp, _dp]
         self._run = {0: L.ref_heat3d, 1: L.ref_heat2d, 2: L.ref_implicit2d,
                      3: L.ref_scalability3d, 4: L.ref_scalability2d, 5: L.ref_implicit3d}
 
@@ -285,6 +287,78 @@ class Ref(_Base):
         rc = self._run[pid](p, elements, dt, nsteps, mode, stage, _d(u), _d(tm))
         assert rc == 0
         return u, tm
+
+
+    def flow(self, p, elements, dt, nsteps, u0=None, stage=0):
+        """examples/flow/flow.hpp through the compiled reference: (u, permeability table at the quadrature
+        points, x fastest).  u0 None: the shipped before(); stage 1: compute_rhs alone."""
+        n, nq = elements + p, elements * (p + 1)
+        kq = np.zeros(nq ** 3)
+        tm = np.zeros(8)
+        if u0 is None:
+            u, mode = np.zeros(n ** 3), 1
+        else:
+            u, mode = np.array(u0, dtype=np.float64).ravel().copy(), 0
+            assert u.size == n ** 3
+        assert self.lib.ref_flow(p, elements, dt, nsteps, mode, stage, _d(u), _d(kq), _d(tm)) == 0
+        return u, kq
+
+
+def pointwise_rhs(tables, u_prev, form, plain=None):
+    """numpy restatement of the reference's element loop for a general pointwise form -- zero(rhs); for e, q:
+    u = eval_fun(u_prev, e, q); for a: rhs(a) += (k0 v + k . grad v) w J  (examples/scalability/test3d.hpp:66-95,
+    examples/flow/flow.hpp:74-101; eval_fun / eval_basis: include/ads/simulation/simulation_3d.hpp:64-136) --
+    written with dense per-axis evaluation matrices B[point, dof], so it shares nothing with the kernels.
+    tables: basis_tables() of every axis; form(u, ux, uy[, uz], x, y[, z]) -> (k0, k1, k2[, k3]) on arrays shaped
+    [x points, y points(, z points)]; plain (optional): the same signature, one array added to every DOF of the
+    point's element WITHOUT the test function (test3d.hpp:86-88).  Returns rhs, first index fastest."""
+    nd = len(tables)
+    B, dB, S, wJ, X = [], [], [], [], []
+    for t in tables:
+        ne, q, _, m = t["b"].shape
+        n = ne + m - 1
+        b, db, sup = np.zeros((ne * q, n)), np.zeros((ne * q, n)), np.zeros((ne * q, n))
+        for e in range(ne):
+            f = int(t["first_dof"][e])
+            b[e * q:(e + 1) * q, f:f + m] = t["b"][e, :, 0, :]
+            db[e * q:(e + 1) * q, f:f + m] = t["b"][e, :, 1, :]
+            sup[e * q:(e + 1) * q, f:f + m] = 1.0
+        B.append(b), dB.append(db), S.append(sup)
+        wJ.append((t["w"][None, :] * t["J"][:, None]).ravel())
+        X.append(t["x"].ravel())
+    shape = tuple(b.shape[1] for b in B)
+    U = np.asarray(u_prev, dtype=np.float64).reshape(shape, order="F")
+    if nd == 3:
+        ev = lambda a, b, c, T: np.einsum("ai,bj,ck,ijk->abc", a, b, c, T, optimize=True)      # noqa: E731
+        tr = lambda a, b, c, K: np.einsum("ai,bj,ck,abc->ijk", a, b, c, K, optimize=True)      # noqa: E731
+        W = wJ[0][:, None, None] * wJ[1][None, :, None] * wJ[2][None, None, :]
+        pts = (X[0][:, None, None], X[1][None, :, None], X[2][None, None, :])
+        vals = (ev(B[0], B[1], B[2], U), ev(dB[0], B[1], B[2], U), ev(B[0], dB[1], B[2], U), ev(B[0], B[1], dB[2], U))
+        k = form(*vals, *pts)
+        rhs = (tr(B[0], B[1], B[2], k[0] * W) + tr(dB[0], B[1], B[2], k[1] * W) + tr(B[0], dB[1], B[2], k[2] * W)
+               + tr(B[0], B[1], dB[2], k[3] * W))
+        if plain is not None:
+            rhs = rhs + tr(S[0], S[1], S[2], np.broadcast_to(plain(*vals, *pts), W.shape) * W)
+    else:
+        ev = lambda a, b, T: np.einsum("ai,bj,ij->ab", a, b, T, optimize=True)      # noqa: E731
+        tr = lambda a, b, K: np.einsum("ai,bj,ab->ij", a, b, K, optimize=True)      # noqa: E731
+        W = wJ[0][:, None] * wJ[1][None, :]
+        pts = (X[0][:, None], X[1][None, :])
+        vals = (ev(B[0], B[1], U), ev(dB[0], B[1], U), ev(B[0], dB[1], U))
+        k = form(*vals, *pts)
+        rhs = tr(B[0], B[1], k[0] * W) + tr(dB[0], B[1], k[1] * W) + tr(B[0], dB[1], k[2] * W)
+        if plain is not None:
+            rhs = rhs + tr(S[0], S[1], np.broadcast_to(plain(*vals, *pts), W.shape) * W)
+    return rhs.ravel(order="F").copy()
+
+
+def flow_form(dt, kq, mi=10.0):
+    """integrand of examples/flow/flow.hpp:74-101 for pointwise_rhs; kq: permeability at the points [x, y, z]"""
+    def form(u, ux, uy, uz, x, y, z):
+        h = 1 + np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y) * np.sin(2 * np.pi * z)
+        e = -dt * kq * np.exp(mi * u)
+        return u + dt * h, e * ux, e * uy, e * uz
+    return form
 
 
 def synthetic_state(shape, seed=20260101):

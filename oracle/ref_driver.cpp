@@ -34,7 +34,9 @@
 #include <iterator>
 #include <memory>
 #include <mutex>
+#include <limits>
 #include <numeric>
+#include <random>
 #include <sstream>
 #include <string>
 #include <string_view>
@@ -55,6 +57,7 @@
 #include "ads/executor/galois.hpp"
 #include "ads/quad/gauss.hpp"
 #include "ads/simulation.hpp"
+#include "flow/flow.hpp"
 #include "heat/heat_2d.hpp"
 #include "heat/heat_3d.hpp"
 #include "implicit/implicit.hpp"
@@ -432,6 +435,53 @@ int ref_scalability2d(int p, int n, double dt, int nsteps, int init_mode, int st
                    [](ads::problems::scalability_2d& s) { s.compute_rhs(); }, call_before{});
     if (timings) timings[1] = static_cast<double>(sim.integration_timer.get_usec()) * 1e-6;
     return rc;
+}
+
+// examples/flow/flow.hpp: nonlinear pointwise form with the permeability tabulated at the quadrature points.
+// kq_out (may be NULL) receives that table, x fastest: kq[(ex*q+kx) + nqx*((ey*q+ky) + nqy*(ez*q+kz))].
+int ref_flow(int p, int n, double dt, int nsteps, int init_mode, int stage, double* u, double* kq_out,
+             double* timings) {
+    ads::dim_config dim{p, n};
+    ads::config_3d c{dim, dim, dim, ads::timesteps_config{nsteps, dt}, 1};
+    ads::problems::flow sim{c};
+    {
+        cout_silencer quiet;
+        sim.fill_permeability_map();
+    }
+    if (kq_out) {
+        const int q = p + 1;
+        const std::size_t nq = static_cast<std::size_t>(n) * q;
+        for (int ez = 0; ez < n; ++ez)
+            for (int ey = 0; ey < n; ++ey)
+                for (int ex = 0; ex < n; ++ex)
+                    for (int kz = 0; kz < q; ++kz)
+                        for (int ky = 0; ky < q; ++ky)
+                            for (int kx = 0; kx < q; ++kx)
+                                kq_out[(ex * q + kx) + nq * ((ey * q + ky) + nq * (static_cast<std::size_t>(ez) * q + kz))] =
+                                    sim.kq(ex, ey, ez, kx, ky, kz);
+    }
+    if (stage == 1 || init_mode == 1)
+        return drive(sim, init_mode, stage, stage == 1 ? nsteps : 0, dt, u, timings,
+                     [](ads::problems::flow& s) { s.compute_rhs(0.0); }, call_before{}) ||
+               (stage == 1 ? 0 : [&] {
+                   copy_in(sim.u, u);
+                   for (int i = 0; i < nsteps; ++i) {
+                       sim.before_step(i, i * dt);
+                       sim.step(i, i * dt);
+                   }
+                   copy_out(sim.u, u);
+                   return 0;
+               }());
+    // after_step() only prints the energy and writes files (flow.hpp:116-123); its iostream formatting is
+    // left out of the step loop here
+    sim.prepare_matrices();
+    copy_in(sim.u, u);
+    for (int i = 0; i < nsteps; ++i) {
+        sim.before_step(i, i * dt);
+        sim.step(i, i * dt);
+    }
+    copy_out(sim.u, u);
+    return 0;
 }
 
 // 3-D implicit extension (see implicit_3d_ref above); stage 1..3 -> compute_rhs_dir(stage-1)

@@ -36,4 +36,4 @@ def golden():
     import numpy as np
 
     d = os.path.join(ROOT, "tests", "golden")
-    return {name: np.load(os.path.join(d, name + ".npz")) for name in ("setup", "solve", "problems")}
+    return {name: np.load(os.path.join(d, name + ".npz")) for name in ("setup", "solve", "problems", "flow")}
