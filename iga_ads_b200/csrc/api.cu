@@ -452,7 +452,7 @@ int quad_axes(adsb_ctx* c, QuadAxes& A) {
 }
 
 
-// General quadrature path: zero the out box, integrate every element that touches it, add gamma * F.
+// General quadrature path (brick kernel): out = gamma * F + the quadrature sums of every element touching the box.
 int rhs_quadrature_impl(adsb_ctx* c, const adsb_form& f, const double* in, const adsb_view& vi, const int* in_lo,
                         const double* forcing, double* out, const adsb_view& vo, const int* out_lo) {
     QuadAxes A;
@@ -461,8 +461,7 @@ int rhs_quadrature_impl(adsb_ctx* c, const adsb_form& f, const double* in, const
     g.in = in;
     g.out = out;
     g.forcing = nullptr;
-    int elo[3] = {0, 0, 0}, en[3] = {1, 1, 1}, on[3] = {1, 1, 1};
-    long long so[3] = {1, 0, 0};
+    int elo[3] = {0, 0, 0}, en[3] = {1, 1, 1};
     for (int d = 0; d < 3; ++d) {
         g.si[d] = vi.s[d];
         g.so[d] = vo.s[d];
@@ -471,8 +470,6 @@ int rhs_quadrature_impl(adsb_ctx* c, const adsb_form& f, const double* in, const
         g.out_lo[d] = out_lo[d];
         g.out_n[d] = vo.n[d];
         g.beta[d] = d < c->ndim ? f.beta[d] : 0.0;
-        so[d] = vo.s[d];
-        on[d] = d < c->ndim ? vo.n[d] : 1;
         if (d < c->ndim) {
             const int p = c->ax[d].p;
             if (c->ax[d].q != p + 1 || c->ax[d].ders != 1)
@@ -488,13 +485,20 @@ int rhs_quadrature_impl(adsb_ctx* c, const adsb_form& f, const double* in, const
     g.gamma = f.gamma;
     if (f.source < 0 || f.source > 1) return fail(ADSB_EINVAL, "compute_rhs: unknown source");
     StageTimer t(c, 0);
-    cudaError_t e = (cudaError_t) launch_zero_box(out, on, so, c->stream);
-    if (e == cudaSuccess) e = (cudaError_t) launch_rhs_quadrature(c->ndim, A, g, f.gamma != 0.0 ? f.source : 0, elo, en, c->stream);
-    c->launches += 2;
-    if (e == cudaSuccess && forcing && f.gamma != 0.0) {
-        e = (cudaError_t) launch_axpy_box(out, forcing, f.gamma, on, so, c->stream);
-        c->launches++;
-    }
+    // brick kernel: out = gamma F (load tensor, if any) + quadrature sums; a built-in source without a load
+    // tensor is evaluated at the points and enters without the test function (test3d.hpp:86-88)
+    PointFormArgs pf{};
+    pf.kind = 0;
+    pf.alpha = f.alpha;
+    for (int d = 0; d < 3; ++d) pf.beta[d] = g.beta[d];
+    pf.gamma = f.gamma;
+    pf.source = (!forcing && f.gamma != 0.0) ? f.source : 0;
+    pf.plain = 1;
+    g.forcing = forcing;
+    g.max_sms = c->sm_limit;
+    int nl = 0;
+    cudaError_t e = (cudaError_t) launch_rhs_brick(c->ndim, A, g, pf, elo, en, nullptr, c->stream, &nl);
+    c->launches += nl;
     if (e != cudaSuccess) return cuda_fail(e, "quadrature rhs kernels");
     return ADSB_OK;
 }

@@ -177,12 +177,6 @@ int launch_element_source(int src, const QuadAxes& A, double* G, const int elo[3
 int launch_box_sum(const QuadAxes& A, const double* G, double* out, const int elo[3], const int en[3],
                    const int lo[3], const int n[3], cudaStream_t st, long long pitch0 = 0);
 
-// General quadrature right-hand side (kernels_quadrhs.cu): elements [elo, elo+en) are integrated and
-// scattered (atomically) into the DOFs of g's out box, which must be zero on entry.  source: built-in
-// pointwise source added as gamma * f(x_q) * w * J to every local DOF (0: none).
-int launch_rhs_quadrature(int ndim, const QuadAxes& A, const RhsGeom& g, int source, const int elo[3], const int en[3],
-                          cudaStream_t st);
-int launch_zero_box(double* y, const int n[3], const long long s[3], cudaStream_t st);
 // Pointwise form of the brick quadrature kernel (quadbrick.cuh); mirrors adsb_point_form.
 struct PointFormArgs {
     int kind;  // 0 linear (+ advection, built-in source), 1 flow (nonlinear, tabulated coefficient)
@@ -194,7 +188,6 @@ struct PointFormArgs {
 // coef: per-point coefficient table of the whole domain (x fastest) for the forms that use one.
 int launch_rhs_brick(int ndim, const QuadAxes& A, const RhsGeom& g, const PointFormArgs& f, const int elo[3],
                      const int en[3], const double* coef, cudaStream_t st, int* nlaunch);
-int launch_axpy_box(double* y, const double* x, double a, const int n[3], const long long s[3], cudaStream_t st);
 
 // Per-line factors (kernels_lines.cu): the special dimension of the generalised ADS.
 int launch_line_sweep(int p, double* t, const double* ab, const int* ipiv, int n, long long lines, int axis, int L0,

@@ -53,6 +53,8 @@ struct PointIn {
     double u, ux, uy, uz;  // u_prev and its gradient at the point
     double x, y, z;        // the point
     double coef;           // the caller's coefficient table at the point (forms with USES_COEF)
+    double col, zf;        // the form's own column_value(x, y) and plane_value(z) (forms with SEPARABLE): factors of
+                           // a separable coefficient, evaluated once per point column / once per z point
 };
 struct PointOut {
     double k0, k1, k2, k3;  // the integrand is k0 v + k1 dv/dx + k2 dv/dy + k3 dv/dz   (before the factor w J)
@@ -64,7 +66,7 @@ struct PointOut {
 // forcing enters without the test function, test3d.hpp:86-88; the advection term is pollution_3d.hpp's)
 template <bool PLAIN_>
 struct FormLinear {
-    static constexpr bool PLAIN = PLAIN_, USES_COEF = false;
+    static constexpr bool PLAIN = PLAIN_, USES_COEF = false, SEPARABLE = false;
     double alpha, beta[3], adv[3], gamma;
     int source;
     __device__ __forceinline__ void operator()(const PointIn& in, PointOut& o, bool d3) const {
@@ -86,10 +88,13 @@ struct FormLinear {
 // examples/flow/flow.hpp:74-101:  (u v + dt (-k(x) exp(mi u) grad u . grad v + h(x) v)) w J, k tabulated at the
 // quadrature points (fill_permeability_map, flow.hpp:53-60)
 struct FormFlow {
-    static constexpr bool PLAIN = false, USES_COEF = true;
+    static constexpr bool PLAIN = false, USES_COEF = true, SEPARABLE = true;
     double dt, mi;
-    __device__ __forceinline__ void operator()(const PointIn& in, PointOut& o, bool d3) const {
-        const double h = source_value(2, d3, in.x, in.y, in.z);
+    // the forcing 1 + sin(2 pi x) sin(2 pi y) sin(2 pi z) (flow.hpp:124-128) in its separable factors
+    __device__ __forceinline__ double column_value(double x, double y) const { return sin(2 * PI * x) * sin(2 * PI * y); }
+    __device__ __forceinline__ double plane_value(double z) const { return sin(2 * PI * z); }
+    __device__ __forceinline__ void operator()(const PointIn& in, PointOut& o, bool) const {
+        const double h = 1 + in.col * in.zf;
         const double e = -dt * in.coef * exp(mi * in.u);
         o.k0 = in.u + dt * h;
         o.k1 = e * in.ux;
@@ -107,13 +112,15 @@ struct BrickGrid {
     long long cq1, cq2;              // its row and plane strides (points)
 };
 
-// brick shape per degree: EX x EY element columns, PT point columns per thread (PT divides q = p + 1)
+// brick shape per degree: EX x EY element columns, PT point columns per thread (PT divides q = p + 1).  The
+// register file is split over the four SM sub-partitions, so what counts is warps per sub-partition:
+// <= 8 warps leave 255 registers per thread, 9 ... 12 warps 168, 13 ... 16 warps 128.
 template <int P> struct BrickCfg;
 template <> struct BrickCfg<1> { static constexpr int EX = 16, EY = 8, PT = 2; };
-template <> struct BrickCfg<2> { static constexpr int EX = 16, EY = 8, PT = 3; };
+template <> struct BrickCfg<2> { static constexpr int EX = 14, EY = 6, PT = 3; };  // 252 threads = 8 warps: 255 registers
 template <> struct BrickCfg<3> { static constexpr int EX = 8, EY = 4, PT = 2; };
 template <> struct BrickCfg<4> { static constexpr int EX = 4, EY = 4, PT = 1; };
-template <> struct BrickCfg<5> { static constexpr int EX = 4, EY = 4, PT = 2; };
+template <> struct BrickCfg<5> { static constexpr int EX = 4, EY = 3, PT = 2; };   // 216 threads
 
 template <int P, bool D3, bool PLAIN>
 struct BrickDims {
@@ -127,14 +134,15 @@ struct BrickDims {
     // shared-memory carve-up (doubles)
     static constexpr int oBx = 0;                        // [2][M][GX]
     static constexpr int oBy = oBx + 2 * M * GX;         // [EY][Q][2][M]
-    static constexpr int oBz = oBy + EY * Q * 2 * M;     // [QZ][2][MZ]
-    static constexpr int oWx = oBz + QZ * 2 * MZ;        // [GX]  w J
+    static constexpr int oBz = oBy + EY * Q * 2 * M;     // [2][QZ][2][MZ]
+    static constexpr int oWx = oBz + 2 * QZ * 2 * MZ;    // [GX]  w J      (the z tables are double-buffered)
     static constexpr int oXx = oWx + GX;                 // [GX]  point coordinates
     static constexpr int oWy = oXx + GX;                 // [GY]
     static constexpr int oXy = oWy + GY;
-    static constexpr int oWz = oXy + GY;                 // [QZ]
-    static constexpr int oXz = oWz + QZ;
-    static constexpr int oC = oXz + QZ;                  // [DYn][DXn]  coefficient plane
+    static constexpr int oWz = oXy + GY;                 // [2][QZ]
+    static constexpr int oXz = oWz + 2 * QZ;
+    static constexpr int oZf = oXz + 2 * QZ;             // [2][QZ]  the form's plane_value(z)
+    static constexpr int oC = oZf + 2 * QZ;              // [DYn][DXn]  coefficient plane
     static constexpr int oV = oC + NC;                   // [DYn][GX]
     static constexpr int oD = oV + DYn * GX;
     static constexpr int oP0 = oD + DYn * GX;            // [NR][M][GX]
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
     quad_brick_kernel(const QuadAxes A, const RhsGeom g, const Form form, const BrickGrid G) {
     using B = BrickDims<P, D3, Form::PLAIN>;
     constexpr int EX = B::EX, EY = B::EY, PT = B::PT, M = B::M, Q = B::Q, NG = B::NG, GX = B::GX, GY = B::GY;
-    constexpr int DXn = B::DXn, DYn = B::DYn, MZ = B::MZ, QZ = B::QZ, PZ = B::PZ, NR = B::NR, NT = B::NT, NC = B::NC;
+    constexpr int DXn = B::DXn, DYn = B::DYn, MZ = B::MZ, QZ = B::QZ, PZ = B::PZ, NT = B::NT, NC = B::NC;
     constexpr bool PLAIN = Form::PLAIN;
     extern __shared__ double sm[];
     double* const sBx = sm + B::oBx;
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
     double* const sXy = sm + B::oXy;
     double* const sWz = sm + B::oWz;
     double* const sXz = sm + B::oXz;
+    double* const sZf = sm + B::oZf;
     double* const sC = sm + B::oC;
     double* const sV = sm + B::oV;
     double* const sD = sm + B::oD;
@@ -208,12 +217,11 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
     // ---- this thread's point columns: gx, element row ey, points qy = s PT .. s PT + PT - 1 of it
     const int gx = tid % GX, r = tid / GX, ey = r / NG, s = r % NG;
     const bool col_ok = (ex0 + gx / Q) < ex_end && (ey0 + ey) < ey_end;
-    double wJxy[PT], py[PT];
-    const double px = sXx[gx];
+    double wJxy[PT], colv[Form::SEPARABLE ? PT : 1];
 #pragma unroll
     for (int t = 0; t < PT; ++t) {
         wJxy[t] = sWx[gx] * sWy[ey * Q + s * PT + t];
-        py[t] = sXy[ey * Q + s * PT + t];
+        if constexpr (Form::SEPARABLE) colv[t] = form.column_value(sXx[gx], sXy[ey * Q + s * PT + t]);
     }
     const double* const byT = sBy + (ey * Q + s * PT) * 2 * M;  // [t][d][j]
     const long long coef_col = G.coef ? (long long) (ex0 * Q + gx) + G.cq1 * (long long) ((ey0 + ey) * Q + s * PT) : 0;
@@ -230,40 +238,61 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
             if (PLAIN) Tp[j][t] = 0.0;
         }
 
-    // coefficient (tid % DXn, tid / DXn) of DOF plane c, zero outside the input box
-    auto load_c = [&](int c) -> double {
-        if (tid >= NC) return 0.0;
-        const int ga = ex0 + tid % DXn, gb = ey0 + tid / DXn;
-        bool ok = ga >= g.in_lo[0] && ga < g.in_lo[0] + g.in_n[0] && gb >= g.in_lo[1] && gb < g.in_lo[1] + g.in_n[1];
-        if (D3) ok = ok && c >= g.in_lo[2] && c < g.in_lo[2] + g.in_n[2];
-        if (!ok) return 0.0;
-        return __ldg(g.in + (long long) (ga - g.in_lo[0]) * g.si[0] + (long long) (gb - g.in_lo[1]) * g.si[1] +
-                     (D3 ? (long long) (c - g.in_lo[2]) * g.si[2] : 0));
+    // ---- the DOF column (a, b) = (tid % DXn, tid / DXn) this thread loads and, later, adds to
+    const int ca = tid % DXn, cb = tid / DXn;
+    const int ga = ex0 + ca, gb = ey0 + cb;
+    const bool in_xy = tid < NC && ga >= g.in_lo[0] && ga < g.in_lo[0] + g.in_n[0] && gb >= g.in_lo[1] && gb < g.in_lo[1] + g.in_n[1];
+    const bool out_xy = tid < NC && ga >= g.out_lo[0] && ga < g.out_lo[0] + g.out_n[0] && gb >= g.out_lo[1] && gb < g.out_lo[1] + g.out_n[1];
+    const double* const src_col = g.in + (long long) (ga - g.in_lo[0]) * g.si[0] + (long long) (gb - g.in_lo[1]) * g.si[1];
+    double* const dst_col = g.out + (long long) (ga - g.out_lo[0]) * g.so[0] + (long long) (gb - g.out_lo[1]) * g.so[1];
+    auto load_c = [&](int c) -> double {  // coefficient of DOF plane c, zero outside the input box
+        if (!in_xy) return 0.0;
+        if (D3 && (c < g.in_lo[2] || c >= g.in_lo[2] + g.in_n[2])) return 0.0;
+        return __ldg(src_col + (D3 ? (long long) (c - g.in_lo[2]) * g.si[2] : 0));
+    };
+    auto out_ptr = [&](int c) -> double* {  // DOF plane c of the output, nullptr outside the out box
+        if (!out_xy) return nullptr;
+        if (D3 && (c < g.out_lo[2] || c >= g.out_lo[2] + g.out_n[2])) return nullptr;
+        return dst_col + (D3 ? (long long) (c - g.out_lo[2]) * g.so[2] : 0);
     };
 
+    // Iteration k:  plane ez0 + k enters (X, Y stages), element ez0 + k - PZ is integrated (Z, form, Z^T), the
+    // partial plane ez0 + k - PZ leaves (Y^T partials).  Its reduction (Y^T sums, X^T, read-modify-write) runs
+    // one iteration later, next to the X stage and at the head of the register phase, so an iteration has two
+    // barriers and the global read-modify-write latency hides behind the X stage.
     const int niter = nez + 2 * PZ;
     double creg = load_c(ez0);
 #pragma unroll 1
-    for (int k = 0; k < niter; ++k) {
-        const bool interp = k < nez + PZ;       // DOF plane ez0 + k enters
-        const int e = k - PZ;                   // element ez0 + e is integrated
-        const bool elem = e >= 0 && e < nez;
-        const bool emit = k >= PZ;              // DOF plane ez0 + k - PZ leaves
-        if (tid < NC) sC[tid] = creg;
+    for (int k = 0; k <= niter; ++k) {
+        const bool live = k < niter;
+        const bool interp = k < nez + PZ;           // DOF plane ez0 + k enters
+        const int e = k - PZ;                       // element ez0 + e is integrated
+        const bool elem = live && e >= 0 && e < nez;
+        const bool emit = live && k >= PZ;          // partial plane ez0 + k - PZ leaves
+        const bool drain = k >= 1 && k - 1 >= PZ;   // the plane that left in iteration k - 1 is reduced now
+        double* const sBzk = sBz + (k & 1) * (QZ * 2 * MZ);
+        double* const sWzk = sWz + (k & 1) * QZ;
+        double* const sXzk = sXz + (k & 1) * QZ;
+        double* const sZfk = sZf + (k & 1) * QZ;
+        if (live && tid < NC) sC[tid] = creg;
         if (elem) {
             if (D3) {
-                for (int i = tid; i < QZ * 2 * MZ; i += NT) sBz[i] = A.bt[2][(size_t) (ez0 + e) * Q * 2 * M + i];
+                for (int i = tid; i < QZ * 2 * MZ; i += NT) sBzk[i] = A.bt[2][(size_t) (ez0 + e) * Q * 2 * M + i];
                 for (int i = tid; i < QZ; i += NT) {
-                    sWz[i] = A.w[2][i] * A.J[2][ez0 + e];
-                    sXz[i] = A.xq[2][(ez0 + e) * Q + i];
+                    sWzk[i] = A.w[2][i] * A.J[2][ez0 + e];
+                    sXzk[i] = A.xq[2][(ez0 + e) * Q + i];
+                    if constexpr (Form::SEPARABLE) sZfk[i] = form.plane_value(A.xq[2][(ez0 + e) * Q + i]);
                 }
             } else if (tid == 0) {
-                sBz[0] = 1.0;  // value
-                sBz[1] = 0.0;  // derivative
-                sWz[0] = 1.0;
-                sXz[0] = 0.0;
+                sBzk[0] = 1.0;  // value
+                sBzk[1] = 0.0;  // derivative
+                sWzk[0] = 1.0;
+                sXzk[0] = 0.0;
+                if constexpr (Form::SEPARABLE) sZfk[0] = form.plane_value(0.0);
             }
         }
+        double* const dst = drain ? out_ptr(ez0 + k - 1 - PZ) : nullptr;
+        const double old = dst ? *dst : 0.0;  // in flight across the X stage
         __syncthreads();
         if (interp && k + 1 < nez + PZ) creg = load_c(ez0 + k + 1);  // in flight during the whole iteration
 
@@ -282,7 +311,50 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
                 sD[j] = d;
             }
         }
+        // ---- Y^T of the previous plane: S(gx, b) = sum over the element rows b - p .. b and their point groups
+        if (drain) {
+            for (int j = tid; j < GX * DYn; j += NT) {
+                const int b = j / GX, x = j % GX;
+                double s0 = 0.0, s1 = 0.0, sp = 0.0;
+#pragma unroll
+                for (int i = 0; i <= P; ++i) {
+                    const int el = b - i;
+                    if (el >= 0 && el < EY) {
+#pragma unroll
+                        for (int gq = 0; gq < NG; ++gq) {
+                            const int rr = el * NG + gq;
+                            s0 += sP0[(rr * M + i) * GX + x];
+                            s1 += sP1[(rr * M + i) * GX + x];
+                            if (PLAIN) sp += sPp[rr * GX + x];
+                        }
+                    }
+                }
+                sS0[j] = s0;
+                sS1[j] = s1;
+                if (PLAIN) sSp[j] = sp;
+            }
+        }
         __syncthreads();
+
+        // ---- X^T of the previous plane and its read-modify-write (bricks of one launch touch disjoint DOFs)
+        if (dst) {
+            double v0 = 0.0, v1 = 0.0, vp = 0.0;
+#pragma unroll
+            for (int i = 0; i <= P; ++i) {
+                const int el = ca - i;
+                if (el >= 0 && el < EX) {
+#pragma unroll
+                    for (int qx = 0; qx < Q; ++qx) {
+                        const int x = el * Q + qx;
+                        v0 = fma(sBx[i * GX + x], sS0[cb * GX + x], v0);
+                        v1 = fma(sBx[(M + i) * GX + x], sS1[cb * GX + x], v1);
+                        if (PLAIN) vp += sSp[cb * GX + x];
+                    }
+                }
+            }
+            *dst = old + ((v0 + v1) + vp);
+        }
+        if (!live) break;
 
         // ---- Y stage into the register window
         if (interp) {
@@ -323,10 +395,10 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
                 double bz[MZ], dbz[MZ];
 #pragma unroll
                 for (int j = 0; j < MZ; ++j) {
-                    bz[j] = sBz[(qz * 2 + 0) * MZ + j];
-                    dbz[j] = sBz[(qz * 2 + 1) * MZ + j];
+                    bz[j] = sBzk[(qz * 2 + 0) * MZ + j];
+                    dbz[j] = sBzk[(qz * 2 + 1) * MZ + j];
                 }
-                const double wz = sWz[qz], pz = sXz[qz];
+                const double wz = sWzk[qz];
 #pragma unroll
                 for (int t = 0; t < PT; ++t) {
                     PointIn in;
@@ -338,10 +410,14 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
                         in.uy = fma(bz[j], Wy[j][t], in.uy);
                         if (D3) in.uz = fma(dbz[j], Ww[j][t], in.uz);
                     }
-                    in.x = px;
-                    in.y = py[t];
-                    in.z = pz;
-                    in.coef = 0.0;
+                    in.x = sXx[gx];
+                    in.y = sXy[ey * Q + s * PT + t];
+                    in.z = sXzk[qz];
+                    in.coef = in.col = in.zf = 0.0;
+                    if constexpr (Form::SEPARABLE) {
+                        in.col = colv[t];
+                        in.zf = sZfk[qz];
+                    }
                     if (Form::USES_COEF) {
                         if (col_ok && G.coef)
                             in.coef = __ldg(G.coef + coef_col + G.cq1 * t + (D3 ? G.cq2 * (long long) ((ez0 + e) * Q + qz) : 0));
@@ -396,53 +472,6 @@ __global__ void __launch_bounds__((BrickDims<P, D3, Form::PLAIN>::NT), 1)
             for (int t = 0; t < PT; ++t) {
                 T0[MZ - 1][t] = T1[MZ - 1][t] = T2[MZ - 1][t] = 0.0;
                 if (PLAIN) Tp[MZ - 1][t] = 0.0;
-            }
-        }
-        __syncthreads();
-
-        // ---- Y^T: S(gx, b) = sum over the element rows b - p .. b and their point groups, in a fixed order
-        if (emit) {
-            for (int j = tid; j < GX * DYn; j += NT) {
-                const int b = j / GX, x = j % GX;
-                double s0 = 0.0, s1 = 0.0, sp = 0.0;
-                const int lo = max(b - P, 0), hi = min(b, EY - 1);
-                for (int el = lo; el <= hi; ++el)
-#pragma unroll
-                    for (int gq = 0; gq < NG; ++gq) {
-                        const int rr = el * NG + gq;
-                        s0 += sP0[(rr * M + (b - el)) * GX + x];
-                        s1 += sP1[(rr * M + (b - el)) * GX + x];
-                        if (PLAIN) sp += sPp[rr * GX + x];
-                    }
-                sS0[j] = s0;
-                sS1[j] = s1;
-                if (PLAIN) sSp[j] = sp;
-            }
-        }
-        __syncthreads();
-
-        // ---- X^T and the plane's read-modify-write (bricks of one launch touch disjoint DOFs)
-        if (emit) {
-            const int c = ez0 + k - PZ;  // global DOF plane
-            const bool cz_ok = !D3 || (c >= g.out_lo[2] && c < g.out_lo[2] + g.out_n[2]);
-            if (tid < NC && cz_ok) {
-                const int a = tid % DXn, b = tid / DXn;
-                const int ga = ex0 + a, gb = ey0 + b;
-                if (ga >= g.out_lo[0] && ga < g.out_lo[0] + g.out_n[0] && gb >= g.out_lo[1] && gb < g.out_lo[1] + g.out_n[1]) {
-                    double val = 0.0;
-                    const int lo = max(a - P, 0), hi = min(a, EX - 1);
-                    for (int el = lo; el <= hi; ++el)
-#pragma unroll
-                        for (int qx = 0; qx < Q; ++qx) {
-                            const int x = el * Q + qx;
-                            val = fma(sBx[(a - el) * GX + x], sS0[b * GX + x], val);
-                            val = fma(sBx[(M + a - el) * GX + x], sS1[b * GX + x], val);
-                            if (PLAIN) val += sSp[b * GX + x];
-                        }
-                    double* dst = g.out + (long long) (ga - g.out_lo[0]) * g.so[0] + (long long) (gb - g.out_lo[1]) * g.so[1] +
-                                  (D3 ? (long long) (c - g.out_lo[2]) * g.so[2] : 0);
-                    *dst += val;
-                }
             }
         }
     }
@@ -508,6 +537,14 @@ int launch_brick(const QuadAxes& A, const RhsGeom& g, const Form& form, const in
 template <class Form>
 int launch_brick_form(int ndim, const QuadAxes& A, const RhsGeom& g, const Form& form, const int elo[3], const int en[3],
                       const double* coef, int max_sms, cudaStream_t st, int* nlaunch);
+
+#define ADSB_BRICK_DECLARE(FORM)                                                                                   \
+    template <>                                                                                                    \
+    int launch_brick_form<FORM>(int ndim, const QuadAxes& A, const RhsGeom& g, const FORM& form, const int elo[3], \
+                                const int en[3], const double* coef, int max_sms, cudaStream_t st, int* nlaunch);
+ADSB_BRICK_DECLARE(FormLinear<false>)
+ADSB_BRICK_DECLARE(FormLinear<true>)
+ADSB_BRICK_DECLARE(FormFlow)
 
 #define ADSB_BRICK_DISPATCH(FORM, MAXP)                                                                             \
     template <>                                                                                                     \

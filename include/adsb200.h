@@ -148,9 +148,9 @@ int adsb_set_plane(adsb_ctx* ctx, int buf, int axis, int idx, const double* valu
  * method ADSB_RHS_COLLAPSED applies the exactly pre-integrated 1-D quadrature operators
  * (sum factorisation carried through the quadrature sums; HBM-bound);
  * method ADSB_RHS_QUADRATURE evaluates u and grad u at every Gauss point and integrates against
- * the test functions by sum factorisation (general pointwise forms; FP64-bound); it zeroes dst and
- * scatter-adds element contributions like zero(rhs) + update_global_rhs
- * (include/ads/simulation/simulation_3d.hpp:140-145), so the summation order is not fixed. */
+ * the test functions by sum factorisation (general pointwise forms; FP64-bound, deterministic): the brick
+ * kernel of adsb_compute_rhs_pointwise with the linear form; it replaces zero(rhs) + the element loop +
+ * update_global_rhs (include/ads/simulation/simulation_3d.hpp:140-145). */
 #define ADSB_RHS_COLLAPSED 0
 #define ADSB_RHS_QUADRATURE 1
 typedef struct {
