@@ -114,6 +114,7 @@ _SIGNATURES = {
     "adsb_basis_tables": (c_int, [c_int, c_int, c_dbl, c_dbl, c_int, c_int, dp, dp, dp, dp, ip]),
     "adsb_matrix_1d": (c_int, [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int, dp]),
     "adsb_band_factorize": (c_int, [c_int, c_int, c_int, dp, c_int, ip]),
+    "adsb_band_unpivot": (c_int, [c_int, c_int, c_int, c_int, dp, ip, dp]),
     "adsb_segment_bounds": (c_int, [c_int, c_int, ip, c_int, c_int, ip]),
     "adsb_segment_plan": (c_int, [c_int, c_int, c_int, c_int, dp, ip, c_int, ip, c_dbl, ip, dp, dp, dp, dp, dp]),
     "adsb_create": (c_int, [c_int, ip, ip, ip, c_int, ctypes.POINTER(vp)]),
@@ -135,6 +136,17 @@ _SIGNATURES = {
     "adsb_row_pitch": (c_ll, [vp]),
     "adsb_set_plane": (c_int, [vp, c_int, c_int, c_int, dp]),
     "adsb_compute_rhs": (c_int, [vp, ctypes.POINTER(Form), c_int, c_int]),
+    "adsb_device_count": (c_int, []),
+    "adsb_slabs_create": (c_int, [c_int, ip, ip, ctypes.POINTER(vp)]),
+    "adsb_slabs_destroy": (c_int, [vp]),
+    "adsb_slabs_set_axis_tables": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, dp, dp, dp, dp, ip]),
+    "adsb_slabs_set_axis_factor": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_int, dp, ip]),
+    "adsb_slabs_commit": (c_int, [vp, ctypes.POINTER(Substep), c_int]),
+    "adsb_slabs_upload": (c_int, [vp, dp]),
+    "adsb_slabs_download": (c_int, [vp, dp]),
+    "adsb_slabs_step": (c_int, [vp, c_int]),
+    "adsb_slabs_synchronize": (c_int, [vp]),
+    "adsb_slabs_info": (c_int, [vp, ip, ip]),
     "adsb_set_line_factors": (c_int, [vp, c_int, c_int, c_int, dp, ip]),
     "adsb_solve_special": (c_int, [vp, c_int, c_int, ip]),
     "adsb_set_point_coefficient": (c_int, [vp, dp]),

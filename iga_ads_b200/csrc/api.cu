@@ -747,6 +747,22 @@ int adsb_set_axis_factor(adsb_ctx* c, int axis, int slot, int n, int kl, int ku,
     if (kl < 0 || ku < 0 || ldab < 2 * kl + ku + 1) return fail(ADSB_EINVAL, "set_axis_factor: bad band shape");
     if (int rc = select_device(c)) return rc;
     static_assert(SWEEP_MAX_DEPTH == SWEEP_MAX_DEPTH_DEV, "depth constants out of sync");
+    // factors with row interchanges are eliminated again without them when that is stable (host_setup.cpp:
+    // refactor_without_pivoting); ADSB_UNPIVOT=0 keeps the caller's interchanges
+    static const bool unpivot = [] {
+        const char* e = getenv("ADSB_UNPIVOT");
+        return !e || atoi(e) != 0;
+    }();
+    std::vector<double> ab2;
+    std::vector<int> ipiv2;
+    bool has_piv = false;
+    for (int j = 0; j < n; ++j) has_piv = has_piv || ipiv[j] != j + 1;
+    if (unpivot && has_piv && refactor_without_pivoting(n, kl, ku, ldab, ab, ipiv, ab2)) {
+        ipiv2.resize(n);
+        for (int j = 0; j < n; ++j) ipiv2[j] = j + 1;
+        ab = ab2.data();
+        ipiv = ipiv2.data();
+    }
     SweepPlan P;
     if (int rc = build_sweep_plan(n, kl, ku, ldab, ab, ipiv, SWEEP_CH, 1, P)) return rc;
     DevFactor& D = c->ax[axis].fac[slot];
@@ -1291,6 +1307,15 @@ int adsb_project_values(adsb_ctx* c, int dst, int ez_lo, int ez_cnt, const doubl
     if (e != cudaSuccess) return cuda_fail(e, "project_values kernel");
     if (e2 != cudaSuccess) return cuda_fail(e2, "project_values kernel");
     c->launches++;
+    return ADSB_OK;
+}
+
+int adsb_band_unpivot(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, double* ab_out) {
+    if (!ab || !ipiv || !ab_out || n < 1 || kl < 0 || ku < 0 || ldab < 2 * kl + ku + 1)
+        return fail(ADSB_EINVAL, "band_unpivot: bad argument");
+    std::vector<double> out;
+    if (!refactor_without_pivoting(n, kl, ku, ldab, ab, ipiv, out)) return 1;
+    std::copy(out.begin(), out.end(), ab_out);
     return ADSB_OK;
 }
 

@@ -268,6 +268,74 @@ int band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// A dgbtrf factor WITH row interchanges widens U to kl + ku super-diagonals and, for the Gram matrices of
+// degree >= 4, lengthens the chunk chains of the substitution kernel until they no longer fit its depth.  The
+// 1-D matrices on this path (Gram, Gram + h * stiffness, with fix_left / fix_right rows) are symmetric
+// positive definite up to those rows, so Gaussian elimination WITHOUT interchanges is backward stable for
+// them.  refactor_without_pivoting rebuilds A = P^T L U from the caller's factor (every entry a sum of at most
+// kl + 1 products: an O(eps) perturbation of A, like dgbtrf's own), eliminates again without interchanges and
+// reports whether that was safe: every multiplier at most 4 in magnitude, no pivot below 1e-8 max|A|.  The
+// solve then is the same linear system with a different, equally stable elimination order; results agree with
+// dgbtrs to rounding (tests: every pivoting factor of the golden set and of the oracle comparisons).
+// ---------------------------------------------------------------------------------------------
+bool refactor_without_pivoting(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv,
+                               std::vector<double>& out) {
+    const int kd = kl + ku;
+    const int M = kl + kd;            // margin: a row i is kept on columns [i - M, i + M]
+    const int W = 2 * M + 1;
+    std::vector<double> X(static_cast<size_t>(n) * W, 0.0);
+    auto at = [&](int i, int c) -> double& { return X[static_cast<size_t>(i) * W + (c - i + M)]; };
+    auto Aat = [&](int r, int c) { return ab[static_cast<size_t>(c) * ldab + r]; };
+    for (int c = 0; c < n; ++c)
+        for (int k = 0; k <= std::min(kd, c); ++k) at(c - k, c) = Aat(kd - k, c);
+    std::vector<double> tmp(W);
+    for (int j = n - 2; j >= 0; --j) {
+        const int lm = std::min(kl, n - 1 - j);
+        const int chi = std::min(n - 1, j + kd);
+        for (int i = 1; i <= lm; ++i) {
+            const double l = Aat(kd + i, j);
+            if (l != 0.0)
+                for (int c = j; c <= chi; ++c) at(j + i, c) += l * at(j, c);
+        }
+        const int pj = ipiv[j] - 1;
+        if (pj < j || pj > j + lm) return false;
+        if (pj != j) {
+            // rows j and pj change places; their entries lie on columns [j - kl, j + kd + kl] at most
+            const int clo = std::max(0, j - kl), chi2 = std::min(n - 1, j + kd + kl);
+            for (int c = clo; c <= chi2; ++c) {
+                const bool in_j = std::abs(c - j) <= M, in_p = std::abs(c - pj) <= M;
+                const double vj = in_j ? at(j, c) : 0.0, vp = in_p ? at(pj, c) : 0.0;
+                if ((!in_j && vp != 0.0) || (!in_p && vj != 0.0)) return false;
+                if (in_j) at(j, c) = vp;
+                if (in_p) at(pj, c) = vj;
+            }
+        }
+    }
+    double amax = 0.0;
+    for (int i = 0; i < n; ++i)
+        for (int c = std::max(0, i - M); c <= std::min(n - 1, i + M); ++c) amax = std::max(amax, std::fabs(at(i, c)));
+    if (!(amax > 0.0)) return false;
+    for (int i = 0; i < n; ++i)
+        for (int c = std::max(0, i - M); c <= std::min(n - 1, i + M); ++c)
+            if ((c < i - kl || c > i + ku) && std::fabs(at(i, c)) > 1e-13 * amax) return false;  // not a (kl, ku) band
+    // elimination without interchanges, in place on the band rows
+    out.assign(static_cast<size_t>(n) * ldab, 0.0);
+    for (int j = 0; j < n; ++j) {
+        const double piv = at(j, j);
+        if (!(std::fabs(piv) >= 1e-8 * amax)) return false;
+        const int lm = std::min(kl, n - 1 - j), cu = std::min(n - 1, j + ku);
+        for (int i = 1; i <= lm; ++i) {
+            const double l = at(j + i, j) / piv;
+            if (!(std::fabs(l) <= 4.0)) return false;
+            out[static_cast<size_t>(j) * ldab + kd + i] = l;
+            for (int c = j + 1; c <= cu; ++c) at(j + i, c) -= l * at(j, c);
+        }
+        for (int k = 0; k <= std::min(ku, j); ++k) out[static_cast<size_t>(j) * ldab + kd - k] = at(j - k, j);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Plan for the chunk-parallel substitution kernel (kernels_sweep.cu).  A line of n unknowns is cut
 // into SC chunks of CH columns.  Each chunk runs the pivoted forward recurrence and then the back
 // substitution from ZERO incoming states (local pass); the exact dgbtrs result is recovered as
@@ -278,7 +346,7 @@ int band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv) {
 // X_c = xfirst_local_c + Xi_first_c delta_c.  All response tables depend only on the factor, so
 // they are tabulated here once.  Because the responses decay, the chains are evaluated to a finite
 // depth D in parallel (delta_c = sum_{d<=D} W_{c,d} Delta_{c-d}); the depth is chosen so that the
-// dropped products are below 1e-22 -- if that needs more than MAX_DEPTH terms the kernel falls
+// dropped products are below 1e-18 -- if that needs more than MAX_DEPTH terms the kernel falls
 // back to the sequential chain (seq = 1).
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -384,7 +452,7 @@ int build_sweep_plan(int n, int kl, int ku, int ldab, const double* ab, const in
     // products of the transfer matrices would cancel catastrophically -> chain sequentially
     bool seq = maxabs(T.data(), static_cast<int>(T.size())) > 1.0 || maxabs(Rm.data(), static_cast<int>(Rm.size())) > 1.0;
     std::vector<double> cur(std::max(KL * KL, KD * KD)), nxt(cur.size());
-    const double tiny = 1e-22;
+    const double tiny = 1e-18;  // dropped chain terms: a hundredth of the unit round-off relative to the data
     for (int c = 0; c < SC; ++c) {
         // forward: delta_c = Delta_{c-1} + T_{c-1} Delta_{c-2} + T_{c-1} T_{c-2} Delta_{c-3} + ...
         if (c >= 2) {

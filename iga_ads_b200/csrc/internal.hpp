@@ -20,6 +20,8 @@ int matrix_from_tables(int kind, double h, int p, int elements, int q, int ders,
                        const double* w, const double* J, double* ab);
 int matrix_1d(int kind, int p, int elements, double a, double b, double h, int fix, double* ab);
 int band_factorize(int n, int kl, int ku, double* ab, int ldab, int* ipiv);
+// Same matrix, eliminated again without row interchanges (host_setup.cpp); false: not safe, keep the pivoted factor
+bool refactor_without_pivoting(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, std::vector<double>& out);
 
 constexpr int SWEEP_MAX_DEPTH = 6;  // longest parallel state chain; beyond it the kernel chains sequentially
 

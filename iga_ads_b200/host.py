@@ -54,6 +54,15 @@ def matrix_1d(kind, p, elements, a=0.0, b=1.0, h=0.0, fix=0):
     return ab
 
 
+def band_unpivot(lu, ipiv, kl, ku):
+    """the factor the sweeps run with when the interchanges of (lu, ipiv) can be dropped safely, else None"""
+    lu = np.ascontiguousarray(lu, dtype=np.float64)
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    out = np.zeros_like(lu)
+    rc = check(_lib.load().adsb_band_unpivot(lu.shape[0], kl, ku, lu.shape[1], d_(lu), i_(ipiv), d_(out)))
+    return out if rc == 0 else None
+
+
 def to_band(dense, kl, ku):
     dense = np.asarray(dense, dtype=np.float64)
     n = dense.shape[0]

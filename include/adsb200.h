@@ -300,6 +300,15 @@ int adsb_rhs_view(adsb_ctx* ctx, const adsb_form* form, const double* in, const 
                   const int* in_lo, const double* forcing, double* out, const adsb_view* vout,
                   const int* out_lo);
 
+/* The factor adsb_set_axis_factor actually sweeps with.  A dgbtrf factor with row interchanges is eliminated
+ * again WITHOUT interchanges when that is stable (the matrices of this path are symmetric positive definite up to
+ * their fix_left / fix_right rows): U keeps ku super-diagonals instead of kl + ku and the chunk chains of the
+ * substitution kernel stay short.  ab_out (n columns of ldab rows, dgbtrf layout, identity pivots) receives it;
+ * returns 0, or 1 when the elimination would not be safe (a multiplier above 4, a pivot below 1e-8 max|A|) and the
+ * caller's interchanges are kept.  Same linear system as lin::solve_with_factorized (include/ads/lin/band_solve.hpp:
+ * 21-31), results agree with dgbtrs to rounding.  ADSB_UNPIVOT=0 in the environment switches the step off. */
+int adsb_band_unpivot(int n, int kl, int ku, int ldab, const double* ab, const int* ipiv, double* ab_out);
+
 /* ---- introspection (used by the CPU test-suite to check the substitution plan without a GPU)
  * Builds the chunked-substitution plan of a factor exactly as adsb_set_axis_factor does and copies
  * it out.  dims[16] = {KL, KD, piv, CH, R, SC, ST, rows, LF, LB, LC, DF, DB, seq, MAX_DEPTH, 0};
@@ -397,6 +406,36 @@ int adsb_seg_tin(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, long lon
 int adsb_seg_correct_view(adsb_ctx* ctx, int axis, int slot, int s_lo, int s_hi, int row_base, const double* in,
                           const adsb_view* vin, double* out, const adsb_view* vout, const double* din,
                           const double* tin_or_x);
+
+/* ================== the z-slab sharded step from one host process (csrc/slab_host.cpp) ==================
+ * `world` ranks; rank r owns a slab of z planes on devices[r].  Distinct devices: neighbours map each other's
+ * memory (peer access over NVLink) and every rank runs right-hand side, x / y sweeps and the fused distributed
+ * z sweep on its own stream, the end-of-sub-step neighbour barrier being stream-event waits.  All ranks on ONE
+ * device: "virtual ranks" sharing it as concurrent streams with world-th of the SMs each (single-GPU testing).
+ * The reference's counterpart is simulation_base::run (src/ads/simulation/simulation_base.cpp:11-20) in one
+ * address space; iga_ads_b200/slab.py is the same step with one process per GPU.
+ * Order of calls: create; set_axis_tables x3 and set_axis_factor for every (axis, slot) the program names (same
+ * arguments as the adsb_ctx entry points, replicated to every rank); commit(program) -- picks the slab bounds
+ * (adsb_segment_bounds of the first z factor), builds the ranks, fails with ADSB_EINVAL when the z factor couples
+ * more than neighbouring slabs (chain depth > 1) or the fused sweep does not fit; upload / step / download.
+ * upload / download: the whole tensor, dense, x fastest (host memory).  step enqueues nsteps time steps and
+ * returns; synchronize waits and reports a timed-out wait of the fused sweep.  Forms with gamma != 0 use the
+ * scalability load tensor (adsb_load_tensor(ctx, 1, 0, .)) of every slab. */
+typedef struct adsb_slabs adsb_slabs;
+int adsb_device_count(void);  /* CUDA devices visible to the process (0: none) */
+int adsb_slabs_create(int world, const int* devices, const int* n_global, adsb_slabs** out);
+int adsb_slabs_destroy(adsb_slabs* s);
+int adsb_slabs_set_axis_tables(adsb_slabs* s, int axis, int p, int elements, int q, int ders, const double* b_flat,
+                               const double* xq, const double* w, const double* J, const int* first_dof);
+int adsb_slabs_set_axis_factor(adsb_slabs* s, int axis, int slot, int n, int kl, int ku, int ldab, const double* ab,
+                               const int* ipiv);
+int adsb_slabs_commit(adsb_slabs* s, const adsb_substep* program, int nsub);
+int adsb_slabs_upload(adsb_slabs* s, const double* host);
+int adsb_slabs_download(adsb_slabs* s, double* host);
+int adsb_slabs_step(adsb_slabs* s, int nsteps);
+int adsb_slabs_synchronize(adsb_slabs* s);
+/* bounds[world + 1] (may be NULL); info4 = {world, virtual ranks (0/1), lines per tile of the fused sweep, kernel launches so far} */
+int adsb_slabs_info(adsb_slabs* s, int* bounds, int* info4);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EX = os.path.join(ROOT, "iga_ads_b200", "examples")
-PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check")
+PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check", "heat_3d_slabs")
 
 
 def build():
@@ -78,3 +78,25 @@ def test_surface_check_value_semantics_projection_norms_sampling():
     r = run("surface_check", 12)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "surface_check OK" in r.stdout
+
+
+@pytest.mark.gpu
+# more than two ranks need slabs thick enough for the z factor to couple neighbours only (~47 rows at p = 2)
+@pytest.mark.parametrize("n,steps,ranks,p", [(12, 100, 2, 2), (200, 2, 4, 2), (150, 3, 3, 2), (96, 2, 2, 3)])
+def test_cxx_slab_host_matches_the_single_gpu_run(n, steps, ranks, p):
+    """the z-slab sharded step driven from one C++17 process (adsb_slabs_*: ranks on one device each when the box has
+    them, else virtual ranks on device 0; fused distributed z sweep, event barriers) against the single-GPU example,
+    and for the BASELINE configs[0] run against the reference's checksum"""
+    build()
+    r = run("heat_3d_slabs", n, steps, ranks, p)
+    assert r.returncode == 0, r.stderr + r.stdout
+    got_sum = checksum(r.stdout)
+    got_norm = float(re.search(r"\|u\|_2 = ([0-9.]+)", r.stdout).group(1))
+    if (n, steps, p) == (12, 100, 2):
+        assert abs(got_sum - 132.96044839648852) < 1e-8
+        assert abs(got_norm - 10.367682819844902) < 1e-9
+    one = run("heat_3d_slabs", n, steps, 1, p)
+    assert one.returncode == 0, one.stderr + one.stdout
+    assert abs(got_sum - checksum(one.stdout)) < 1e-10 * max(1.0, abs(got_sum))
+    want_norm = float(re.search(r"\|u\|_2 = ([0-9.]+)", one.stdout).group(1))
+    assert abs(got_norm - want_norm) < 1e-11 * want_norm

@@ -235,3 +235,39 @@ def test_output_writers_follow_the_reference_formats():
     rows = s.getvalue().splitlines()
     assert rows[1] == "      0.0000000000      1.0000000000      2.0000000000"
     assert rows[3] == "      0.5000000000      0.0000000000      4.0000000000" and len(rows) == 6
+
+
+@pytest.mark.parametrize("p,ne,kind,h,fix", [(4, 9, 0, 0.0, 0), (5, 6, 0, 0.0, 0), (5, 43, 0, 0.0, 1), (4, 60, 0, 0.0, 3),
+                                             (4, 9, 3, 3.0, 1), (5, 300, 0, 0.0, 1), (5, 40, 3, 0.02, 0), (4, 768, 0, 0.0, 1)])
+def test_unpivoted_refactorisation_solves_like_dgbtrs(oracle, p, ne, kind, h, fix):
+    """adsb_band_unpivot: the factor the sweeps really use for matrices whose dgbtrf factor has row interchanges
+    (every Gram matrix of degree >= 4) solves the same system as the oracle's dgbtrs with the original factor"""
+    from iga_ads_b200.host import band_unpivot
+
+    n = ne + p
+    ab = ads.matrix_1d(kind, p, ne, h=h, fix=fix)
+    lu, piv = ads.band_factorize(ab, p, p)
+    assert (piv != np.arange(1, n + 1)).any(), "this case is meant to pivot"
+    lu2 = band_unpivot(lu, piv, p, p)
+    if kind == 3 and h >= 1.0 and fix:
+        # fix_left leaves column 0 of a stiffness-dominated K with entries >> 1 under a unit pivot: multipliers
+        # above the bound, the elimination is refused and the caller's interchanges stay
+        assert lu2 is None
+        return
+    assert lu2 is not None
+    assert np.abs(lu2[:, 2 * p + 1:]).max() <= 4.0                 # multipliers
+    assert np.all(lu2[:, :p] == 0.0)                               # U keeps ku super-diagonals: no fill rows
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((7, n))
+    want = oracle.solve_factorized(lu, piv, p, p, b).reshape(7, n)
+    got = oracle.solve_factorized(lu2, np.arange(1, n + 1, dtype=np.int32), p, p, b).reshape(7, n)
+    cond = 1.0
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-12 * cond
+    # and the chunk plan of the unpivoted factor is a parallel chain within the kernel's depth
+    dims = np.zeros(16, dtype=np.int32)
+    from iga_ads_b200 import _lib
+    _lib.check(_lib.load().adsb_sweep_plan(n, p, p, 3 * p + 1, _lib.d_(lu2), _lib.i_(np.arange(1, n + 1, dtype=np.int32)),
+                                           _lib.i_(dims), None, None, None, None, None, None, None, None))
+    assert dims[2] == 0 and dims[1] == p
+    if kind == 0:
+        assert dims[13] == 0, "Gram factors must not need the sequential chain"
