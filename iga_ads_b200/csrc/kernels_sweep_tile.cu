@@ -286,7 +286,11 @@ encode_fn_t encode_fn() {
 bool make_map(CUtensorMap* m, const double* base, int L0, int rows, int L1, long long sj, long long s1, int NL) {
     encode_fn_t enc = encode_fn();
     if (!enc) return false;
-    if (sj <= 0) sj = 2;  // single row: any valid stride
+    if (sj <= 0) {
+        if (rows > 1) return false;  // rows running backwards or on top of each other: not a tensor map; the
+                                     // caller falls back to the register-path kernel
+        sj = 2;                      // single row: any valid stride
+    }
     const cuuint64_t dims[3] = {(cuuint64_t) L0, (cuuint64_t) rows, (cuuint64_t) (L1 > 0 ? L1 : 1)};
     const cuuint64_t strides[2] = {(cuuint64_t) sj * 8, (cuuint64_t) (L1 > 1 ? s1 : sj * rows) * 8};
     const cuuint32_t box[3] = {(cuuint32_t) NL, (cuuint32_t) rows, 1};

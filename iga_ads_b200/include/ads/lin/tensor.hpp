@@ -148,6 +148,38 @@ void zero(tensor<T, Rank>& t) {  // include/ads/lin/tensor/tensor.hpp:44-50
     t.fill_with_zeros();
 }
 
+// Non-owning view with the same indexing (include/ads/lin/tensor/view.hpp, as_tensor): host memory only.
+template <typename T, std::size_t Rank>
+class tensor_view {
+public:
+    using size_array = std::array<int, Rank>;
+    tensor_view(T* data, const size_array& sizes) : data_{data}, sizes_{sizes} { }
+    T* data() const { return data_; }
+    int size(int dim) const { return sizes_[dim]; }
+    const size_array& sizes() const { return sizes_; }
+    int size() const {
+        int n = 1;
+        for (int s : sizes_) n *= s;
+        return n;
+    }
+    template <typename... Idx>
+    T& operator()(Idx... idx) const {
+        static_assert(sizeof...(Idx) == Rank, "wrong number of indices");
+        const int ix[Rank] = {static_cast<int>(idx)...};
+        std::size_t lin = 0;
+        for (std::size_t d = Rank; d-- > 0;) lin = lin * sizes_[d] + ix[d];  // first index fastest
+        return data_[lin];
+    }
+
+private:
+    T* data_;
+    size_array sizes_;
+};
+template <typename T, std::size_t Rank>
+tensor_view<T, Rank> as_tensor(T* data, const std::array<int, Rank>& sizes) {
+    return {data, sizes};
+}
+
 using vector = tensor<double, 1>;
 
 }  // namespace ads::lin

@@ -7,6 +7,7 @@
 
 #include "ads/basis_data.hpp"
 #include "ads/bspline/bspline.hpp"
+#include "ads/executor/galois.hpp"
 #include "ads/executor/sequential.hpp"
 #include "ads/lin/band_matrix.hpp"
 #include "ads/lin/tensor.hpp"

@@ -293,6 +293,20 @@ public:
         }
         return u;
     }
+    // element-local right-hand side and its scatter (simulation_3d.hpp:138-145, simulation_2d.hpp:133-140): what an
+    // example's own host-side compute_rhs() loop uses -- zero(rhs); for e: U = element_rhs(); ...;
+    // update_global_rhs(rhs, U, e).  Such a loop compiles and runs unchanged against these headers (on the host;
+    // the tensor's device copy is refreshed on the next device call); the device forms replace it for speed.
+    index_type local_shape() const {
+        index_type s{};
+        for (std::size_t d = 0; d < D; ++d) s[d] = dims_[d].basis.dofs_per_element();
+        return s;
+    }
+    vector_type element_rhs() const { return vector_type{local_shape()}; }
+    void update_global_rhs(vector_type& global, const vector_type& local, index_type e) const {
+        for (auto a : dofs_on_element(e)) v_at(global, a) += v_at(local, dof_global_to_local(e, a));
+    }
+
     double grad_dot(const value_type& a, const value_type& b) const {
         if constexpr (D == 2)
             return a.dx * b.dx + a.dy * b.dy;

@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EX = os.path.join(ROOT, "iga_ads_b200", "examples")
-PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check", "heat_3d_slabs")
+PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check", "heat_3d_slabs", "element_loop_check", "implicit_3d", "scalability_2d")
 
 
 def build():
@@ -100,3 +100,21 @@ def test_cxx_slab_host_matches_the_single_gpu_run(n, steps, ranks, p):
     assert abs(got_sum - checksum(one.stdout)) < 1e-10 * max(1.0, abs(got_sum))
     want_norm = float(re.search(r"\|u\|_2 = ([0-9.]+)", one.stdout).group(1))
     assert abs(got_norm - want_norm) < 1e-11 * want_norm
+
+
+@pytest.mark.parametrize("p,ne,threads", [(2, 6, 1), (3, 5, 3), (2, 9, 4)])
+def test_reference_style_host_element_loop_runs_unchanged(oracle, p, ne, threads):
+    """no GPU: a compute_rhs() written exactly like examples/scalability/test3d.hpp:66-95 (galois_executor::for_each,
+    element_rhs, eval_fun / eval_basis / grad_dot, synchronized + update_global_rhs, tensor_view) compiled against
+    the C++17 headers reproduces the oracle's right-hand side of the same problem"""
+    build()
+    r = run("element_loop_check", p, ne, threads)
+    assert r.returncode == 0, r.stderr + r.stdout
+    got_sum = float(re.search(r"sum\(rhs\) = (-?[0-9.eE+-]+)", r.stdout).group(1))
+    got_norm = float(re.search(r"\|rhs\|_2 = ([0-9.eE+-]+)", r.stdout).group(1))
+    n = ne + p
+    i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    u_prev = (np.sin(0.3 * i) + 0.5 * np.cos(0.2 * j) + 0.1 * k).ravel(order="F")
+    want, _ = oracle.run("scalability_3d", p, ne, 1e-6, 1, u0=u_prev, stage=1)
+    assert abs(got_sum - want.sum()) < 1e-12 * np.abs(want).sum()
+    assert abs(got_norm - np.linalg.norm(want)) < 1e-12 * np.linalg.norm(want)

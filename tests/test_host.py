@@ -211,6 +211,14 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(ads.AdsbError):
         sim = ads.heat_3d(2, 4, ads.timesteps_config(1, 1e-7))
         sim.prepare_matrices()
+    # the one-process slab host (adsb_slabs_*) refuses as loudly, and reports no devices
+    lib = _lib.load()
+    assert lib.adsb_device_count() == 0
+    h = ctypes.c_void_p()
+    dev = np.zeros(2, dtype=np.int32)
+    n = np.array([14, 14, 14], dtype=np.int32)
+    assert lib.adsb_slabs_create(2, _lib.i_(dev), _lib.i_(n), ctypes.byref(h)) == -2
+    assert b"no CUDA device" in lib.adsb_last_error()
 
 
 def test_output_writers_follow_the_reference_formats():
