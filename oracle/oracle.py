@@ -352,6 +352,43 @@ def pointwise_rhs(tables, u_prev, form, plain=None):
     return rhs.ravel(order="F").copy()
 
 
+def kronecker_heat_rhs(oracle, p, elements, dt, u):
+    """the explicit heat right-hand side (examples/heat/heat_3d.hpp:49-67) WITHOUT any element loop:
+    rhs = (Mx (x) My (x) Mz) u - dt (Sx (x) My (x) Mz + Mx (x) Sy (x) Mz + Mx (x) My (x) Sz) u with the oracle's own 1-D
+    Gram / stiffness matrices (src/ads/form_matrix.cpp:8-42) as scipy sparse matrices applied axis by axis -- an
+    independent route to the same numbers (equal to the oracle's element loop to 8e-16 at 12^3, see
+    tests/test_oracle.py) that is cheap enough for the full 514^3 tensor (~30 s, ~9 GB)."""
+    import scipy.sparse as sp
+
+    n = elements + p
+
+    def csr(ab):
+        rows, cols, vals = [], [], []
+        for j in range(n):
+            for i in range(max(0, j - p), min(n, j + p + 1)):
+                rows.append(i), cols.append(j), vals.append(ab[j, 2 * p + i - j])
+        return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+
+    M, S = csr(oracle.matrix_1d(0, p, elements)), csr(oracle.matrix_1d(1, p, elements))
+    U = np.asarray(u, dtype=np.float64).reshape(n, n, n)      # [z][y][x]: x fastest in memory
+
+    def apply(A, T, axis):
+        if axis == 0:
+            return (A @ T.reshape(n, -1)).reshape(T.shape)
+        if axis == 2:
+            return (T.reshape(-1, n) @ A.T).reshape(T.shape)
+        out = np.empty_like(T)
+        for k in range(n):
+            out[k] = A @ T[k]
+        return out
+
+    X, XS = apply(M, U, 2), apply(S, U, 2)
+    Y, YS, YX = apply(M, X, 1), apply(S, X, 1), apply(M, XS, 1)
+    del X, XS
+    out = apply(M, Y, 0) - dt * (apply(M, YX, 0) + apply(M, YS, 0) + apply(S, Y, 0))
+    return out.ravel()
+
+
 def flow_form(dt, kq, mi=10.0):
     """integrand of examples/flow/flow.hpp:74-101 for pointwise_rhs; kq: permeability at the points [x, y, z]"""
     def form(u, ux, uy, uz, x, y, z):

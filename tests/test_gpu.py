@@ -267,6 +267,38 @@ def test_full_size_512_properties():
     assert rel_l2(outs[2], 0.5 * outs[0] + outs[1]) < 1e-12
 
 
+def test_full_size_514_solve_vs_oracle_dgbtrs(oracle):
+    """K2 at the headline size: ads_solve on the full 514^3 tensor against the oracle's dgbtrs + rotations
+    (~12 s of CPU) -- catches what the property tests cannot (a wrong-but-linear sweep)"""
+    p, ne = 2, 512
+    n = ne + p
+    m = ads.matrix_1d(0, p, ne)
+    lu, piv = ads.band_factorize(m, p, p)
+    rhs = np.random.default_rng(4).standard_normal(n ** 3)
+    want = oracle.ads_solve((n,) * 3, [lu] * 3, [piv] * 3, [p] * 3, [p] * 3, rhs)
+    ctx = make_ctx((n,) * 3, [m] * 3, [p] * 3, [p] * 3)
+    ctx.upload(U, rhs)
+    ctx.solve(U)
+    assert rel_l2(ctx.download(U), want) < TOL_STEP
+
+
+def test_full_size_514_rhs_vs_independent_kronecker_apply(oracle):
+    """K1 at the headline size: the collapsed right-hand side of heat_3d p=2 512^3 against the oracle's 1-D Gram /
+    stiffness matrices applied axis by axis with scipy (oracle.kronecker_heat_rhs, pinned to the oracle's element
+    loop on CPU) -- catches a wrong stiffness coefficient or table at full size"""
+    from oracle.oracle import kronecker_heat_rhs
+
+    p, ne, dt = 2, 512, 1e-7
+    sim = make_problem("heat_3d", p, ne, dt)
+    n = ne + p
+    u0 = np.random.default_rng(6).standard_normal(n ** 3)
+    sim.ctx.upload(U_PREV, u0)
+    sim.ctx.compute_rhs(sim.substeps()[0].form, U_PREV, U)
+    got = sim.ctx.download(U)
+    sim.ctx.close()
+    assert rel_l2(got, kronecker_heat_rhs(oracle, p, ne, dt, u0)) < 1e-13
+
+
 def test_step_keeps_constants_for_pure_mass_form():
     """rhs with beta = 0 followed by the solve is the identity on any state (2-D, p=3, ragged n)."""
     sim = make_problem("implicit_2d", 3, 301, 1e-2)

@@ -181,3 +181,15 @@ def test_live_reference_agrees(oracle, ref):
         a, _ = oracle.run(name, p, ne, dt, 2, u0=u0)
         b, _ = ref.run(name, p, ne, dt, 2, u0=u0)
         assert rel_l2(a, b) < 1e-14, name
+
+
+def test_kronecker_heat_rhs_equals_the_element_loop(oracle):
+    """pins oracle.kronecker_heat_rhs (the independent full-size check of K1, tests/test_gpu.py) to the oracle's
+    restatement of heat_3d.hpp:49-67"""
+    from oracle.oracle import kronecker_heat_rhs, rel_l2, synthetic_state
+
+    for p, ne in ((2, 12), (3, 7)):
+        n = ne + p
+        u0 = synthetic_state((n,) * 3)
+        want, _ = oracle.run("heat_3d", p, ne, 1e-7, 1, u0=u0, stage=1)
+        assert rel_l2(kronecker_heat_rhs(oracle, p, ne, 1e-7, u0), want) < 5e-15
