@@ -1,7 +1,7 @@
-// element_loop_check -- a reference-style compute_rhs() written exactly as examples/scalability/test3d.hpp:66-95
-// writes it (executor.for_each over elements(), element_rhs(), eval_fun / eval_basis / grad_dot,
-// executor.synchronized + update_global_rhs), compiled against these headers and run ON THE HOST: the part of the
-// class surface an unchanged example needs for its own element loops.  No GPU is touched.
+// element_loop_check -- a host-side compute_rhs() in the reference's idiom (the structure of
+// examples/scalability/test3d.hpp:66-95: executor.for_each over elements(), element_rhs(), eval_fun / eval_basis /
+// grad_dot, executor.synchronized + update_global_rhs), compiled against these headers and run ON THE HOST: the
+// part of the class surface an example needs to keep its own element loops.  No GPU is touched.
 //     element_loop_check [p] [elements] [threads]     prints sum(rhs) and |rhs|_2 for the synthetic input
 //     u_prev(i, j, k) = sin(0.3 i) + 0.5 cos(0.2 j) + 0.1 k   (tests compare with the oracle on the same input)
 #include <cmath>
@@ -32,27 +32,30 @@ public:
         return std::exp(-r) + 1 + std::cos(pi * x) * std::cos(pi * y) * std::cos(pi * z);
     }
 
-    const vector_type& compute_rhs() {  // test3d.hpp:66-95
-        auto& rhs = u;
-        zero(rhs);
-        executor.for_each(elements(), [&](index_type e) {
-            auto U = element_rhs();
-            double J = jacobian(e);
-            for (auto q : quad_points()) {
-                double w = weight(q);
-                auto x = point(e, q);
-                value_type u = eval_fun(u_prev, e, q);
-                for (auto a : dofs_on_element(e)) {
-                    auto aa = dof_global_to_local(e, a);
-                    value_type v = eval_basis(e, q, a);
-                    double gradient_prod = grad_dot(u, v);
-                    double val = u.val * v.val - steps.dt * (gradient_prod - forcing(x[0], x[1], x[2]));
-                    U(aa[0], aa[1], aa[2]) += val * w * J;
+    // The element loop in the reference's idiom: every element integrates into its own local tensor, the executor
+    // serialises the scatter.  Integrand of the scalability example: u v - dt (grad u . grad v - f).
+    const vector_type& compute_rhs() {
+        vector_type& out = u;
+        zero(out);
+        const double dt = steps.dt;
+        auto integrate_element = [&](index_type elem) {
+            vector_type local = element_rhs();
+            const double jac = jacobian(elem);
+            for (auto qp : quad_points()) {
+                const double wj = weight(qp) * jac;
+                const auto pt = point(elem, qp);
+                const double f = forcing(pt[0], pt[1], pt[2]);
+                const value_type prev = eval_fun(u_prev, elem, qp);
+                for (auto dof : dofs_on_element(elem)) {
+                    const value_type test = eval_basis(elem, qp, dof);
+                    const index_type at = dof_global_to_local(elem, dof);
+                    local(at[0], at[1], at[2]) += (prev.val * test.val - dt * (grad_dot(prev, test) - f)) * wj;
                 }
             }
-            executor.synchronized([&]() { update_global_rhs(rhs, U, e); });
-        });
-        return rhs;
+            executor.synchronized([&] { update_global_rhs(out, local, elem); });
+        };
+        executor.for_each(elements(), integrate_element);
+        return out;
     }
 };
 

@@ -104,7 +104,7 @@ def test_cxx_slab_host_matches_the_single_gpu_run(n, steps, ranks, p):
 
 @pytest.mark.parametrize("p,ne,threads", [(2, 6, 1), (3, 5, 3), (2, 9, 4)])
 def test_reference_style_host_element_loop_runs_unchanged(oracle, p, ne, threads):
-    """no GPU: a compute_rhs() written exactly like examples/scalability/test3d.hpp:66-95 (galois_executor::for_each,
+    """no GPU: a compute_rhs() in the idiom of examples/scalability/test3d.hpp:66-95 (galois_executor::for_each,
     element_rhs, eval_fun / eval_basis / grad_dot, synchronized + update_global_rhs, tensor_view) compiled against
     the C++17 headers reproduces the oracle's right-hand side of the same problem"""
     build()
