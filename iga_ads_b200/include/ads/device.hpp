@@ -71,8 +71,19 @@ public:
         return slot;
     }
 
+    // which line-factor table (generalised ADS) the context holds on `axis`
+    bool line_factors_current(int axis, const void* owner, unsigned long long version) const {
+        return line_owner_[axis] == owner && line_version_[axis] == version;
+    }
+    void line_factors_uploaded(int axis, const void* owner, unsigned long long version) {
+        line_owner_[axis] = owner;
+        line_version_[axis] = version;
+    }
+
 private:
     adsb_ctx* h_ = nullptr;
+    std::array<const void*, 3> line_owner_{};
+    std::array<unsigned long long, 3> line_version_{};
     int next_buf_ = 0;
     std::vector<int> free_bufs_;
     std::array<std::vector<std::uint64_t>, 3> slots_;

@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EX = os.path.join(ROOT, "iga_ads_b200", "examples")
-PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check", "heat_3d_slabs", "element_loop_check", "implicit_3d", "scalability_2d")
+PROGS = ("heat_3d", "heat_2d", "implicit_2d", "scalability_3d", "surface_check", "heat_3d_slabs", "element_loop_check", "implicit_3d", "scalability_2d", "generalised_ads")
 
 
 def build():
