@@ -113,7 +113,12 @@ int adsb_set_axis_tables(adsb_ctx* ctx, int axis, int p, int elements, int q, in
                          const int* first_dof);
 
 /* Upload a factorised band matrix (output of adsb_band_factorize / dgbtrf_) into `slot` of `axis`.
- * Replaces ads::dim_data{M, ctx} (include/ads/solver.hpp:17-20). */
+ * Replaces ads::dim_data{M, ctx} (include/ads/solver.hpp:17-20).  kl, ku <= 5.  What the sweeps do with it:
+ * a factor with row interchanges is eliminated again without them when that is stable (adsb_band_unpivot);
+ * lines of more than 576 rows are cut into segments by the library (adsb_set_axis_segments semantics); a factor
+ * whose segments cannot be cut (boundary responses that grow: strongly stiffness-dominated matrices) keeps the
+ * unsegmented register-path kernel, which handles lines of up to 4608 rows -- longer lines with such a factor
+ * make adsb_sweep / adsb_solve fail with ADSB_EINVAL (the reference has no such limit). */
 int adsb_set_axis_factor(adsb_ctx* ctx, int axis, int slot, int n, int kl, int ku, int ldab,
                          const double* ab, const int* ipiv);
 
